@@ -1,0 +1,130 @@
+/*
+ * rtc_b200.h -- C-ABI of the B200-native hw5 path tracer hot path (librtc_b200.so).
+ *
+ * Drop-in boundary for FeggieBoss/raytracing-course hw5: every entry point below replaces one
+ * reference interface (cited as file:line under /root/reference/hw5).  Plain pointers and
+ * sizes only; no C++/torch types cross this boundary.  All functions return 0 (RTC_OK) or a
+ * negative rtc_status; rtc_last_error() gives the message for the calling thread.  There is
+ * NO CPU fallback: without a CUDA device every compute entry point fails with
+ * RTC_ERR_NO_DEVICE.
+ *
+ * Buffers named *_host are host pointers, *_dev are device pointers on the scene's device.
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ */
+#ifndef RTC_B200_H
+#define RTC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtc_scene rtc_scene;
+
+typedef enum {
+    RTC_OK = 0,
+    RTC_ERR_IO = -1,          /* cannot open / read / write a file */
+    RTC_ERR_NO_DEVICE = -2,   /* no CUDA device, or device index out of range */
+    RTC_ERR_CUDA = -3,        /* a CUDA runtime call failed (message in rtc_last_error) */
+    RTC_ERR_ARG = -4,         /* bad argument */
+    RTC_ERR_UNSUPPORTED = -5  /* scene exceeds a documented limit (DESIGN.md "Limits") */
+} rtc_status;
+
+/* traversal selection for rtc_intersect* and rtc_set_traversal */
+#define RTC_TRAVERSAL_INDEX   0  /* index BVH + reference-recursion emulation (default, fast) */
+#define RTC_TRAVERSAL_REFTREE 1  /* walks the reference's own BVH node by node (slow, exact twin) */
+
+const char* rtc_last_error(void);
+int rtc_version(void);
+int rtc_device_count(void);
+
+/* ---- Scene::Load + Scene::InitScene  (src/sceneload.cpp:112-176, src/scene.cpp:7-40,
+ *      src/main.cpp:9-15).  Parses the hw5 text format on the host, reproduces the reference's
+ *      primitive order and SAH BVH (src/bvh.cpp:99-179), builds the index BVH, and uploads the
+ *      flattened SoA scene to `device` (HBM) once.  device < 0: host-only scene (parse/build
+ *      only; compute calls fail with RTC_ERR_NO_DEVICE). */
+rtc_scene* rtc_scene_load(const char* path, int device);
+rtc_scene* rtc_scene_parse(const char* text, long len, int device);
+void rtc_scene_free(rtc_scene* s);
+/* re-upload the already built host scene to its device (bench e2e: the per-step H2D copy).
+ * returns the number of bytes copied through *h2d_bytes. */
+int rtc_scene_upload(rtc_scene* s, uint64_t* h2d_bytes);
+
+/* out: width,height,ray_depth,samples,nprims,nbvh(non-plane prims),nnodes(reference BVH),nlights */
+int rtc_scene_info(const rtc_scene* s, uint32_t out[8]);
+/* out: index-BVH nodes, index-BVH depth, reference-BVH depth, units(reference leaves),
+ *      device bytes of the scene, LCA table levels, 0, 0 */
+int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]);
+/* DIMENSIONS / SAMPLES / RAY_DEPTH overrides (value < 0 keeps the file's) */
+int rtc_scene_override(rtc_scene* s, int width, int height, int samples, int ray_depth);
+/* final primitive order after std::partition + the BVH sorts (scene.cpp:17, bvh.cpp:129,168):
+ * original file index of every slot; and the per-primitive record type,material + 26 floats
+ * (col3 emission3 pos3 rot4(xyzw) ior d0(3) d1(3) d2(3) pad3) */
+int rtc_scene_prim_order(const rtc_scene* s, int32_t* out_orig_index_host);
+int rtc_scene_prims(const rtc_scene* s, int32_t* type_material_host, float* data_host);
+/* reference BVH (BVH_t::nodes, bvh.h:30-36) in vector order: aabb_min3 aabb_max3 per node and
+ * left,right,first_primitive_id,primitive_count */
+int rtc_scene_nodes(const rtc_scene* s, float* aabb_host, uint32_t* links_host);
+uint32_t rtc_scene_root(const rtc_scene* s);
+void rtc_set_traversal(rtc_scene* s, int mode);
+
+/* ---- Scene::RayIntersection (src/scene.cpp:46-77) = planes + BVH_t::Intersect
+ *      (src/bvh.cpp:181-225) + Primitive::Intersect (src/primitives.cpp:14-174), n rays.
+ *      o,d: 3 floats per ray.  id = -1 on a miss (t, normal, interior then 0). */
+int rtc_intersect(const rtc_scene* s, long n, const float* o_host, const float* d_host,
+                  int32_t* id_host, float* t_host, float* normal_host, int32_t* interior_host, int mode);
+/* ---- Primitive::Intersect (src/primitives.cpp:14-52) of one primitive (final-order id) */
+int rtc_primitive_intersect(const rtc_scene* s, int prim, long n, const float* o_host, const float* d_host,
+                            int32_t* hit_host, float* t_host, float* normal_host, int32_t* interior_host);
+/* ---- Camera::GetToRay (src/scene.cpp:180-187): xy = 2 floats per ray */
+int rtc_camera_rays(const rtc_scene* s, long n, const float* xy_host, float* o_host, float* d_host);
+/* ---- Distribution::Pdf of Scene::mix_distrib (src/distributions.cpp:401-416, 289-372) */
+int rtc_mix_pdf(const rtc_scene* s, long n, const float* x_host, const float* nrm_host, const float* d_host,
+                float* pdf_host);
+/* ---- Distribution::Sample of Scene::mix_distrib (src/distributions.cpp:385-399, 144-159,
+ *      227-269, 318-338) with the Philox stream (seed, pixel = ray index, sample, bounce) */
+int rtc_mix_sample(const rtc_scene* s, long n, const float* x_host, const float* nrm_host,
+                   uint32_t seed, uint32_t sample, uint32_t bounce, float* dir_host);
+/* ---- AcesTonemap + GammaCorrected + Color::toUInts (src/color.cpp:26-49) */
+int rtc_tonemap_u8(const rtc_scene* s, long npix, const float* rgb_host, uint8_t* out_host);
+
+/* ---- Scene::Render (src/scene.cpp:205-252) / Scene::Sample (:189-203) / Scene::RayTrace
+ *      (:83-178), as a wavefront integrator.
+ * rtc_render_accumulate adds, for every pixel, the radiance of samples
+ * [sample_begin, sample_begin+sample_count) into accum_dev (3 floats per pixel, row-major,
+ * device memory, NOT cleared here).  Samples use disjoint counter-based RNG streams, so N
+ * ranks rendering disjoint sample ranges and summing their buffers (NCCL reduce) reproduce
+ * the single-GPU image.  Asynchronous on `stream`; counters are valid after
+ * rtc_render_counters (which synchronises the stream). */
+int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t sample_count,
+                          float* accum_dev, void* stream);
+/* out: paths, rays (RayIntersection calls), launches (kernels launched), wavefront batches,
+ *      index-BVH node visits and (slot 6) primitive tests (only with rtc_set_profiling
+ *      count_visits), slot 5 fallback rays, 0 -- totals since
+ * the scene was created or rtc_render_reset_counters. */
+int rtc_render_counters(rtc_scene* s, void* stream, uint64_t out[8]);
+int rtc_render_reset_counters(rtc_scene* s);
+/* mean = 1/total_samples * sum ; tonemap ; gamma ; u8 -> rgb_dev (3 bytes per pixel, device) */
+int rtc_render_resolve(rtc_scene* s, const float* accum_dev, uint32_t total_samples, uint8_t* rgb_dev, void* stream);
+/* whole Scene::Render with the scene's own SAMPLES: host u8 image (3*W*H bytes) */
+int rtc_render_u8(rtc_scene* s, uint32_t seed, uint8_t* rgb_host);
+/* linear per-pixel radiance SUM over a sample range, copied to the host (parity tests) */
+int rtc_render_sum(rtc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t sample_count, float* sum_host);
+/* run.sh <scene> <out.ppm> in one call: "P6\nW H\n255\n" + bytes (src/scene.cpp:206-208,243-251) */
+int rtc_render_ppm(rtc_scene* s, uint32_t seed, const char* out_path);
+/* Instrumentation (off by default).  kernel_events: bracket every wavefront kernel with CUDA
+ * events on the launching stream; count_visits: use the extend-kernel variant that counts
+ * index-BVH node visits and primitive tests (counters 4 and 6 of rtc_render_counters).
+ * rtc_render_profile synchronises `stream` and returns total milliseconds and launch counts per
+ * kernel class: 0 generate, 1 extend (Scene::RayIntersection), 2 shade, 3 other. */
+int rtc_set_profiling(rtc_scene* s, int kernel_events, int count_visits);
+int rtc_render_profile(rtc_scene* s, void* stream, double ms[4], uint64_t launches[4], int reset);
+/* wavefront batch size in paths (0 = default); takes effect at the next render call */
+int rtc_set_batch_paths(rtc_scene* s, uint64_t paths);
+
+/* Philox4x32-10 block (the RNG of the render path), host-side, for known-answer tests */
+void rtc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

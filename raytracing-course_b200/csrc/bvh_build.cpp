@@ -1,0 +1,327 @@
+// bvh_build.cpp -- Scene::InitScene on the host: primitive order, the reference's SAH BVH, the
+// light list, then OUR acceleration data (index BVH over the reference's leaves + an LCA table)
+// and the flattening into float4 arrays for HBM.
+//
+// Why two trees.  The reference's traversal result depends on its BVH topology: a primitive is
+// tested only if the ray passes the AABB test of every ancestor, where a node is skipped when
+// `closest_dist < t_enter && !interior` (src/bvh.cpp:185-198) and closest_dist is the hit
+// distance found in the left sibling subtree.  Because IntersectTriangle intersects the plane
+// through the LOCAL ORIGIN (src/primitives.cpp:155-157), hit points do not lie inside the AABBs
+// and that skipping rule changes results, so a drop-in replacement has to reproduce it.  On the
+// dragon scenes every triangle has POSITION 0 0 0, the sort keys are all equal, and the
+// resulting tree is nearly useless for culling (~1100 node visits per primary ray on 10k
+// triangles).  We therefore keep the reference tree only as the DEFINITION of the result and
+// find the leaves a ray touches with a second, spatially good BVH (index BVH); the reference
+// recursion is then replayed on just those leaves, using lowest-common-ancestor queries on
+// the reference tree (DESIGN.md "Traversal").
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+#include "scene_host.h"
+
+namespace rtc {
+
+static const float kInf = 1e18f;  // include/bvh.h:9
+
+static Aabb empty_box() { return Aabb{{kInf, kInf, kInf}, {-kInf, -kInf, -kInf}}; }
+static void grow(Aabb& b, vec3 p) {  // AABB_t::Extend(Point) src/bvh.cpp:29-34
+    b.mx.x = std::max(b.mx.x, p.x); b.mn.x = std::min(b.mn.x, p.x);
+    b.mx.y = std::max(b.mx.y, p.y); b.mn.y = std::min(b.mn.y, p.y);
+    b.mx.z = std::max(b.mx.z, p.z); b.mn.z = std::min(b.mn.z, p.z);
+}
+static void grow(Aabb& b, const Aabb& o) { grow(b, o.mx); grow(b, o.mn); }  // src/bvh.cpp:36-39
+static float surface(const Aabb& b) {                                        // src/bvh.cpp:23-27
+    vec3 d = b.mx - b.mn;
+    return 2.f * (d.x * d.y + d.x * d.z + d.y * d.z);
+}
+
+Aabb aabb_of_primitive(const Primitive& p) {
+    vec3 lo, hi;
+    if (p.type == PT_TRIANGLE) {
+        lo = mk3(std::min({p.d0.x, p.d1.x, p.d2.x}), std::min({p.d0.y, p.d1.y, p.d2.y}), std::min({p.d0.z, p.d1.z, p.d2.z}));
+        hi = mk3(std::max({p.d0.x, p.d1.x, p.d2.x}), std::max({p.d0.y, p.d1.y, p.d2.y}), std::max({p.d0.z, p.d1.z, p.d2.z}));
+    } else if (p.type == PT_BOX || p.type == PT_ELLIPSOID) {
+        lo = -1.f * p.d0;
+        hi = p.d0;
+    } else {
+        throw std::runtime_error("aabb_of_primitive: primitive type has no bounding box");
+    }
+    Aabb b = empty_box();
+    for (int corner = 0; corner < 8; ++corner) {
+        vec3 v = mk3((corner & 1) ? hi.x : lo.x, (corner & 2) ? hi.y : lo.y, (corner & 4) ? hi.z : lo.z);
+        grow(b, rotate(p.rot, v));
+    }
+    b.mn = b.mn + p.pos;
+    b.mx = b.mx + p.pos;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-order SAH BVH (BVH_t::InitTree, src/bvh.cpp:105-179).  Works on a permutation of
+// primitive indices; std::sort / std::partition are the very library routines the reference
+// calls, with an equivalent comparator, so equal keys end up in the same order as there.
+namespace {
+struct RefBuilder {
+    std::vector<RefNode>& nodes;
+    std::vector<int32_t>& perm;
+    const std::vector<Aabb>& box;         // per original primitive
+    const std::vector<Primitive>& prims;  // original order
+    std::vector<float> cost;
+
+    void sort_axis(uint32_t first, uint32_t last, int axis) {
+        const Primitive* P = prims.data();
+        std::sort(perm.begin() + first, perm.begin() + last,
+                  [P, axis](int32_t a, int32_t b) { return idx(P[a].pos, axis) < idx(P[b].pos, axis); });
+    }
+
+    uint32_t build(uint32_t first, uint32_t last) {
+        Aabb all = empty_box();
+        for (uint32_t i = first; i < last; ++i) grow(all, box[perm[i]]);
+        uint32_t me = (uint32_t)nodes.size();
+        nodes.push_back(RefNode{all, UINT32_MAX, UINT32_MAX, first, last - first});
+        if (last - first == 1) return me;
+
+        float best[3] = {kInf, kInf, kInf};
+        uint32_t where[3] = {0, 0, 0};
+        for (int axis = 0; axis < 3; ++axis) {
+            sort_axis(first, last, axis);
+            // cost[cut] = S(first..cut-1) * (cut-first) + S(cut..last-1) * (last-cut)
+            Aabb left = box[perm[first]];
+            for (uint32_t cut = first + 1; cut < last; ++cut) {
+                cost[cut] = surface(left) * (cut - first);
+                grow(left, box[perm[cut]]);
+            }
+            Aabb right = empty_box();
+            for (uint32_t cut = last - 1; cut > first; --cut) {
+                grow(right, box[perm[cut]]);
+                cost[cut] += surface(right) * (last - cut);
+            }
+            for (uint32_t cut = first + 1; cut < last; ++cut)
+                if (cost[cut] < best[axis]) { best[axis] = cost[cut]; where[axis] = cut; }
+        }
+        float optimum = std::min({best[0], best[1], best[2]});
+        float leaf_cost = surface(all) * (last - first);
+        if (optimum >= leaf_cost) return me;
+
+        uint32_t cut = 0;
+        for (int axis = 0; axis < 3; ++axis) {
+            if (optimum == best[axis]) {
+                sort_axis(first, last, axis);  // re-sort: moves equal keys again, exactly as the reference does
+                cut = where[axis];
+                break;
+            }
+        }
+        uint32_t l = build(first, cut);
+        nodes[me].left = l;
+        uint32_t r = build(cut, last);
+        nodes[me].right = r;
+        return me;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Index BVH: a plain binary SAH tree over the reference's LEAVES ("units").  Every unit keeps
+// exactly the AABB the reference stores for that leaf; traversal reports all units whose AABB
+// the ray touches (no ordering, no early out -- see the header comment).
+struct Unit {
+    Aabb box;
+    uint32_t first, count;
+    vec3 centre;
+};
+struct IndexBuilder {
+    const std::vector<Unit>& units;
+    std::vector<uint32_t> order;
+    std::vector<f4>& out;  // 4 f4 per node
+    std::vector<float> rarea;
+    uint32_t max_depth = 0;
+
+    static uint32_t leaf_ref(const Unit& u) { return IREF_LEAF | ((u.count - 1) << 24) | u.first; }
+    static f4 bits4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        f4 r;
+        std::memcpy(&r.x, &a, 4); std::memcpy(&r.y, &b, 4); std::memcpy(&r.z, &c, 4); std::memcpy(&r.w, &d, 4);
+        return r;
+    }
+    Aabb bound(uint32_t lo, uint32_t hi) const {
+        Aabb b = empty_box();
+        for (uint32_t i = lo; i < hi; ++i) grow(b, units[order[i]].box);
+        return b;
+    }
+    // returns the child reference for units order[lo..hi)
+    uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth) {
+        max_depth = std::max(max_depth, depth);
+        if (hi - lo == 1) return leaf_ref(units[order[lo]]);
+        float best = 3.0e38f;
+        int best_axis = -1;
+        uint32_t best_cut = 0;
+        for (int axis = 0; axis < 3; ++axis) {
+            std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
+                float ca = idx(units[a].centre, axis), cb = idx(units[b].centre, axis);
+                return ca < cb || (ca == cb && a < b);
+            });
+            Aabb r = empty_box();
+            for (uint32_t i = hi - 1; i > lo; --i) { grow(r, units[order[i]].box); rarea[i] = surface(r); }
+            Aabb l = empty_box();
+            for (uint32_t i = lo + 1; i < hi; ++i) {
+                grow(l, units[order[i - 1]].box);
+                float c = surface(l) * (i - lo) + rarea[i] * (hi - i);
+                if (c < best) { best = c; best_axis = axis; best_cut = i; }
+            }
+        }
+        if (best_axis != 2)
+            std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
+                float ca = idx(units[a].centre, best_axis), cb = idx(units[b].centre, best_axis);
+                return ca < cb || (ca == cb && a < b);
+            });
+        uint32_t me = (uint32_t)(out.size() / 4);
+        out.resize(out.size() + 4);
+        Aabb lb = bound(lo, best_cut), rb = bound(best_cut, hi);
+        uint32_t lref = build(lo, best_cut, depth + 1);
+        uint32_t rref = build(best_cut, hi, depth + 1);
+        out[4 * me + 0] = f4{lb.mn.x, lb.mn.y, lb.mn.z, lb.mx.x};
+        out[4 * me + 1] = f4{lb.mx.y, lb.mx.z, rb.mn.x, rb.mn.y};
+        out[4 * me + 2] = f4{rb.mn.z, rb.mx.x, rb.mx.y, rb.mx.z};
+        out[4 * me + 3] = bits4(lref, rref, 0, 0);
+        return me;
+    }
+};
+}  // namespace
+
+static f4 pack(vec3 v, uint32_t bits) {
+    f4 r{v.x, v.y, v.z, 0.f};
+    std::memcpy(&r.w, &bits, 4);
+    return r;
+}
+
+void HostScene::init() {
+    const uint32_t n = (uint32_t)prims.size();
+    if (n >= IREF_MAX_PRIMS) throw std::runtime_error("scene has more than 2^24 primitives");
+
+    // ---- Scene::InitBVH (src/scene.cpp:16-21): non-planes first (std::partition order)
+    std::vector<Primitive> original = prims;
+    std::vector<int32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0);
+    const Primitive* P = original.data();
+    nbvh = (uint32_t)(std::partition(perm.begin(), perm.end(), [P](int32_t i) { return P[i].type != PT_PLANE; }) - perm.begin());
+
+    nodes.clear();
+    root = 0;
+    if (nbvh > 0) {
+        std::vector<Aabb> boxes(n, empty_box());
+        for (uint32_t i = 0; i < n; ++i)
+            if (original[i].type != PT_PLANE) boxes[i] = aabb_of_primitive(original[i]);
+        nodes.reserve(2 * (size_t)nbvh);
+        RefBuilder rb{nodes, perm, boxes, original, std::vector<float>((size_t)nbvh + 1, 0.f)};
+        root = rb.build(0, nbvh);
+    }
+    for (uint32_t i = 0; i < n; ++i) prims[i] = original[perm[i]];
+
+    // ---- Scene::InitDistribution (src/scene.cpp:27-40)
+    lights.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        const Primitive& p = prims[i];
+        if (!(p.emission.x > 0 || p.emission.y > 0 || p.emission.z > 0)) continue;
+        if (p.type == PT_BOX || p.type == PT_ELLIPSOID) lights.push_back((int32_t)i);
+    }
+
+    // ---- flatten primitives
+    FlatScene& F = flat;
+    F = FlatScene();
+    F.geo0.resize(n); F.geo1.resize(n); F.geo2.resize(n);
+    F.xf_pos.resize(n); F.xf_rot.resize(n); F.mat0.resize(n); F.mat1.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const Primitive& p = prims[i];
+        uint32_t flags = (uint32_t)p.type & PF_TYPE_MASK;
+        bool rot_ident = p.rot.x == 0.f && p.rot.y == 0.f && p.rot.z == 0.f && p.rot.w == 1.f;
+        bool pos_zero = p.pos.x == 0.f && p.pos.y == 0.f && p.pos.z == 0.f;
+        if (rot_ident) flags |= PF_ROT_IDENT;
+        if (rot_ident && pos_zero) flags |= PF_IDENT;
+        if (p.type == PT_TRIANGLE) {
+            // n = normalize(cross(b - a, c - a)), src/primitives.cpp:156 -- same float operations,
+            // evaluated once here instead of once per intersection test
+            vec3 nrm = normalize(cross(p.d1 - p.d0, p.d2 - p.d0));
+            F.geo0[i] = f4{p.d0.x, p.d0.y, p.d0.z, nrm.x};
+            F.geo1[i] = f4{p.d1.x, p.d1.y, p.d1.z, nrm.y};
+            F.geo2[i] = f4{p.d2.x, p.d2.y, p.d2.z, nrm.z};
+        } else {
+            F.geo0[i] = f4{p.d0.x, p.d0.y, p.d0.z, 0.f};
+            F.geo1[i] = f4{0, 0, 0, 0};
+            F.geo2[i] = f4{0, 0, 0, 0};
+        }
+        F.xf_pos[i] = pack(p.pos, flags);
+        F.xf_rot[i] = f4{p.rot.x, p.rot.y, p.rot.z, p.rot.w};
+        F.mat0[i] = pack(p.col, (uint32_t)p.material);
+        F.mat1[i] = f4{p.emission.x, p.emission.y, p.emission.z, p.ior};
+    }
+    F.lights = lights;
+
+    // ---- reference tree: centre/half boxes (AABB_t::Intersect, src/bvh.cpp:89-93), depth, cuts
+    const uint32_t nn = (uint32_t)nodes.size();
+    F.rnodes.resize(2 * (size_t)nn);
+    F.rmeta.resize(nn);
+    std::vector<uint32_t> depth(nn, 0);
+    std::vector<Unit> units;
+    if (nn > 0) {
+        std::vector<uint32_t> stack{root};
+        while (!stack.empty()) {
+            uint32_t v = stack.back();
+            stack.pop_back();
+            const RefNode& nd = nodes[v];
+            vec3 half = 0.5f * (nd.box.mx - nd.box.mn);
+            vec3 centre = 0.5f * (nd.box.mx + nd.box.mn);
+            F.rnodes[2 * v] = pack(centre, nd.left);
+            F.rnodes[2 * v + 1] = pack(half, nd.right);
+            F.ref_depth = std::max(F.ref_depth, depth[v]);
+            if (nd.left == UINT32_MAX) {
+                F.rmeta[v] = u4{nd.first, nd.count, depth[v], 0};
+                if (nd.count > IREF_MAX_LEAF_PRIMS) throw std::runtime_error("a BVH leaf holds more than 128 primitives");
+                if (nd.count > 0) units.push_back(Unit{nd.box, nd.first, nd.count, 0.5f * (nd.box.mx + nd.box.mn)});
+            } else {
+                F.rmeta[v] = u4{nd.first, nodes[nd.right].first, depth[v], 0};
+                depth[nd.left] = depth[nd.right] = depth[v] + 1;
+                stack.push_back(nd.right);
+                stack.push_back(nd.left);
+            }
+        }
+    }
+    std::sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.first < b.first; });
+    F.units = (uint32_t)units.size();
+
+    // ---- index BVH
+    F.inodes.clear();
+    F.iroot = IREF_NONE;
+    if (!units.empty()) {
+        IndexBuilder ib{units, {}, F.inodes, std::vector<float>(units.size() + 1, 0.f)};
+        ib.order.resize(units.size());
+        std::iota(ib.order.begin(), ib.order.end(), 0u);
+        F.iroot = ib.build(0, (uint32_t)units.size(), 0);
+        F.index_depth = ib.max_depth;
+    }
+
+    // ---- LCA table: for a cut position c (boundary between primitive c-1 and c) the inner node
+    // that splits there; range-min by depth over positions gives the lowest common ancestor of
+    // two leaves.  lca[l * nbvh + c] = shallowest node among positions c .. c + 2^l - 1.
+    F.lca.clear();
+    F.lca_levels = 0;
+    if (nbvh > 1) {
+        uint32_t levels = 1;
+        while ((1u << levels) < nbvh) ++levels;
+        F.lca_levels = levels;
+        F.lca.assign((size_t)levels * nbvh, UINT32_MAX);
+        for (uint32_t v = 0; v < nn; ++v)
+            if (nodes[v].left != UINT32_MAX) F.lca[F.rmeta[v].y] = v;
+        auto dep = [&](uint32_t v) { return v == UINT32_MAX ? UINT32_MAX : depth[v]; };
+        for (uint32_t l = 1; l < levels; ++l) {
+            const uint32_t* prev = &F.lca[(size_t)(l - 1) * nbvh];
+            uint32_t* cur = &F.lca[(size_t)l * nbvh];
+            uint32_t half = 1u << (l - 1);
+            for (uint32_t c = 0; c < nbvh; ++c) {
+                uint32_t a = prev[c], b = (c + half < nbvh) ? prev[c + half] : UINT32_MAX;
+                cur[c] = dep(b) < dep(a) ? b : a;
+            }
+        }
+    }
+}
+
+}  // namespace rtc

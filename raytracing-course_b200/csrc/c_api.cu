@@ -1,0 +1,608 @@
+// c_api.cu -- the C-ABI of include/rtc_b200.h: scene handle, HBM residency, the wavefront
+// render loop, and host-buffer convenience wrappers.  No CPU fallback anywhere: a compute call
+// on a scene without a device fails with RTC_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "device_scene.h"
+#include "rt_kernels.h"
+#include "rtc_b200.h"
+#include "scene_host.h"
+
+using namespace rtc;
+
+namespace {
+thread_local std::string g_error;
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(RTC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+constexpr uint64_t kDefaultBatchPaths = 1ull << 23;
+constexpr int kMaxDepthSlots = 64;
+}  // namespace
+
+struct rtc_scene {
+    HostScene host;
+    int device = -1;
+    int sms = 0;
+    int traversal = RTC_TRAVERSAL_INDEX;
+    uint64_t batch_paths = kDefaultBatchPaths;
+    uint64_t device_bytes = 0;
+    // scene arrays in HBM
+    DevBuf<float4> geo0, geo1, geo2, xf_pos, xf_rot, mat0, mat1, inodes, rnodes;
+    DevBuf<uint4> rmeta;
+    DevBuf<uint32_t> lca;
+    DevBuf<int32_t> lights;
+    // wavefront state
+    DevBuf<float4> path[2][4];
+    DevBuf<float4> hit_tn;
+    DevBuf<uint32_t> hit_id;
+    DevBuf<uint32_t> queue;              // kMaxDepthSlots words
+    DevBuf<unsigned long long> stats;    // 8 words
+    DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
+    DevBuf<uint8_t> rgb;
+    uint64_t launches = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    bool count_visits = false;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[4] = {0, 0, 0, 0};      // generate, extend, shade, other
+    uint64_t prof_launches[4] = {0, 0, 0, 0};
+
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void span_begin(int kind, cudaStream_t st) {
+        if (!profiling) return;
+        Span sp{get_event(), get_event(), kind};
+        cudaEventRecord(sp.a, st);
+        spans.push_back(sp);
+    }
+    void span_end(cudaStream_t st) {
+        if (!profiling) return;
+        cudaEventRecord(spans.back().b, st);
+    }
+    void collect_spans() {
+        for (Span& sp : spans) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+                prof_ms[sp.kind] += ms;
+                prof_launches[sp.kind] += 1;
+            }
+            event_pool.push_back(sp.a);
+            event_pool.push_back(sp.b);
+        }
+        spans.clear();
+    }
+
+    DevScene dev() const {
+        DevScene S;
+        std::memset(&S, 0, sizeof S);
+        S.geo0 = geo0.p; S.geo1 = geo1.p; S.geo2 = geo2.p; S.xf_pos = xf_pos.p; S.xf_rot = xf_rot.p;
+        S.mat0 = mat0.p; S.mat1 = mat1.p; S.inodes = inodes.p; S.rnodes = rnodes.p; S.rmeta = rmeta.p;
+        S.lca = lca.p; S.lights = lights.p;
+        S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
+        S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
+        S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;
+        S.width = host.cam.width; S.height = host.cam.height; S.ray_depth = host.ray_depth;
+        S.cam_pos = make_float3(host.cam.pos.x, host.cam.pos.y, host.cam.pos.z);
+        S.cam_right = make_float3(host.cam.right.x, host.cam.right.y, host.cam.right.z);
+        S.cam_up = make_float3(host.cam.up.x, host.cam.up.y, host.cam.up.z);
+        S.cam_forward = make_float3(host.cam.forward.x, host.cam.forward.y, host.cam.forward.z);
+        // Camera::GetToRay, src/scene.cpp:181-182 (tan evaluated in double, as the reference's
+        // unqualified tan() does; checked bit-exact against it in tests/)
+        float tx = (float)std::tan((double)(host.cam.fov_x / 2));
+        S.tan_fov_x = tx;
+        S.tan_fov_y = tx * (float)host.cam.height / (float)host.cam.width;
+        S.bg = make_float3(host.background.x, host.background.y, host.background.z);
+        return S;
+    }
+    void release_device() {
+        geo0.release(); geo1.release(); geo2.release(); xf_pos.release(); xf_rot.release(); mat0.release(); mat1.release();
+        inodes.release(); rnodes.release(); rmeta.release(); lca.release(); lights.release();
+        for (auto& set : path) for (auto& b : set) b.release();
+        hit_tn.release(); hit_id.release(); queue.release(); stats.release(); accum.release(); rgb.release();
+        collect_spans();
+        for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
+        event_pool.clear();
+    }
+};
+
+namespace {
+
+template <class T, class H>
+int upload(DevBuf<T>& dst, const std::vector<H>& src, uint64_t& bytes) {
+    static_assert(sizeof(T) == sizeof(H), "layout mismatch");
+    CU(dst.ensure(src.size() ? src.size() : 1));
+    if (!src.empty()) CU(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(H), cudaMemcpyHostToDevice));
+    bytes += src.size() * sizeof(H);
+    return RTC_OK;
+}
+
+int upload_scene(rtc_scene* s, uint64_t* h2d) {
+    if (s->device < 0) return fail(RTC_ERR_NO_DEVICE, "scene has no CUDA device");
+    CU(cudaSetDevice(s->device));
+    const FlatScene& F = s->host.flat;
+    uint64_t bytes = 0;
+    int rc;
+    if ((rc = upload(s->geo0, F.geo0, bytes))) return rc;
+    if ((rc = upload(s->geo1, F.geo1, bytes))) return rc;
+    if ((rc = upload(s->geo2, F.geo2, bytes))) return rc;
+    if ((rc = upload(s->xf_pos, F.xf_pos, bytes))) return rc;
+    if ((rc = upload(s->xf_rot, F.xf_rot, bytes))) return rc;
+    if ((rc = upload(s->mat0, F.mat0, bytes))) return rc;
+    if ((rc = upload(s->mat1, F.mat1, bytes))) return rc;
+    if ((rc = upload(s->inodes, F.inodes, bytes))) return rc;
+    if ((rc = upload(s->rnodes, F.rnodes, bytes))) return rc;
+    if ((rc = upload(s->rmeta, F.rmeta, bytes))) return rc;
+    if ((rc = upload(s->lca, F.lca, bytes))) return rc;
+    if ((rc = upload(s->lights, F.lights, bytes))) return rc;
+    CU(s->queue.ensure(kMaxDepthSlots));
+    if (!s->stats.p) {
+        CU(s->stats.ensure(8));
+        CU(cudaMemset(s->stats.p, 0, 8 * sizeof(unsigned long long)));
+    }
+    s->device_bytes = bytes;
+    if (h2d) *h2d = bytes;
+    return RTC_OK;
+}
+
+rtc_scene* make_scene(const std::string& text, int device) {
+    rtc_scene* s = new rtc_scene();
+    try {
+        s->host.parse(text);
+        s->host.init();
+    } catch (const std::exception& e) {
+        fail(RTC_ERR_UNSUPPORTED, e.what());
+        delete s;
+        return nullptr;
+    }
+    if (s->host.ray_depth + 2 > (unsigned)kMaxDepthSlots) {
+        fail(RTC_ERR_UNSUPPORTED, "RAY_DEPTH above 62 is not supported");
+        delete s;
+        return nullptr;
+    }
+    if (s->host.flat.ref_depth + 1 >= 96) {
+        fail(RTC_ERR_UNSUPPORTED, "reference BVH deeper than 95 levels is not supported");
+        delete s;
+        return nullptr;
+    }
+    s->device = device;
+    if (device >= 0) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) {
+            fail(RTC_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " is not available");
+            delete s;
+            return nullptr;
+        }
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, device);
+        s->sms = prop.multiProcessorCount;
+        if (upload_scene(s, nullptr) != RTC_OK) {
+            s->release_device();
+            delete s;
+            return nullptr;
+        }
+    }
+    return s;
+}
+
+int need_device(const rtc_scene* s) {
+    if (!s) return fail(RTC_ERR_ARG, "null scene");
+    if (s->device < 0) return fail(RTC_ERR_NO_DEVICE, "scene was created without a CUDA device; there is no CPU path");
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return fail(RTC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return RTC_OK;
+}
+
+// temporary device copies of host arrays for the probe entry points
+struct Staged {
+    std::vector<void*> ptrs;
+    ~Staged() { for (void* p : ptrs) cudaFree(p); }
+    template <class T>
+    T* in(const T* host, size_t n) {
+        T* d = nullptr;
+        if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        if (n && cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return d;
+    }
+    template <class T>
+    T* out(size_t n) {
+        T* d = nullptr;
+        if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        return d;
+    }
+};
+#define NEED(ptr) if (!(ptr)) return fail(RTC_ERR_CUDA, "device staging allocation/copy failed")
+
+int ensure_wavefront(rtc_scene* s, uint64_t cap) {
+    for (auto& set : s->path) for (auto& b : set) CU(b.ensure(cap));
+    CU(s->hit_tn.ensure(cap));
+    CU(s->hit_id.ensure(cap));
+    return RTC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtc_last_error(void) { return g_error.c_str(); }
+int rtc_version(void) { return 100; }
+int rtc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+rtc_scene* rtc_scene_parse(const char* text, long len, int device) {
+    if (!text || len < 0) { fail(RTC_ERR_ARG, "null scene text"); return nullptr; }
+    return make_scene(std::string(text, (size_t)len), device);
+}
+rtc_scene* rtc_scene_load(const char* path, int device) {
+    if (!path) { fail(RTC_ERR_ARG, "null path"); return nullptr; }
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { fail(RTC_ERR_IO, std::string("cannot open scene file ") + path); return nullptr; }
+    std::ostringstream ss;
+    ss << in.rdbuf();
+    return make_scene(ss.str(), device);
+}
+void rtc_scene_free(rtc_scene* s) {
+    if (!s) return;
+    if (s->device >= 0) { cudaSetDevice(s->device); s->release_device(); }
+    delete s;
+}
+int rtc_scene_upload(rtc_scene* s, uint64_t* h2d_bytes) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    return upload_scene(s, h2d_bytes);
+}
+int rtc_scene_info(const rtc_scene* s, uint32_t out[8]) {
+    if (!s || !out) return fail(RTC_ERR_ARG, "null argument");
+    out[0] = s->host.cam.width; out[1] = s->host.cam.height; out[2] = s->host.ray_depth; out[3] = s->host.samples;
+    out[4] = (uint32_t)s->host.prims.size(); out[5] = s->host.nbvh; out[6] = (uint32_t)s->host.nodes.size();
+    out[7] = (uint32_t)s->host.lights.size();
+    return RTC_OK;
+}
+int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]) {
+    if (!s || !out) return fail(RTC_ERR_ARG, "null argument");
+    const FlatScene& F = s->host.flat;
+    out[0] = F.inodes.size() / 4; out[1] = F.index_depth; out[2] = F.ref_depth; out[3] = F.units;
+    out[4] = s->device_bytes; out[5] = F.lca_levels; out[6] = 0; out[7] = 0;
+    return RTC_OK;
+}
+int rtc_scene_override(rtc_scene* s, int width, int height, int samples, int ray_depth) {
+    if (!s) return fail(RTC_ERR_ARG, "null scene");
+    if (ray_depth >= 0 && ray_depth + 2 > kMaxDepthSlots) return fail(RTC_ERR_UNSUPPORTED, "RAY_DEPTH above 62 is not supported");
+    if (width >= 0) s->host.cam.width = (unsigned)width;
+    if (height >= 0) s->host.cam.height = (unsigned)height;
+    if (samples >= 0) s->host.samples = (unsigned)samples;
+    if (ray_depth >= 0) s->host.ray_depth = (unsigned)ray_depth;
+    return RTC_OK;
+}
+int rtc_scene_prim_order(const rtc_scene* s, int32_t* out) {
+    if (!s || !out) return fail(RTC_ERR_ARG, "null argument");
+    for (size_t i = 0; i < s->host.prims.size(); ++i) out[i] = s->host.prims[i].orig;
+    return RTC_OK;
+}
+int rtc_scene_prims(const rtc_scene* s, int32_t* tm, float* d) {
+    if (!s || !tm || !d) return fail(RTC_ERR_ARG, "null argument");
+    for (size_t i = 0; i < s->host.prims.size(); ++i) {
+        const Primitive& p = s->host.prims[i];
+        tm[2 * i] = p.type; tm[2 * i + 1] = p.material;
+        float* o = d + 26 * i;
+        const float v[26] = {p.col.x, p.col.y, p.col.z, p.emission.x, p.emission.y, p.emission.z, p.pos.x, p.pos.y, p.pos.z,
+                             p.rot.x, p.rot.y, p.rot.z, p.rot.w, p.ior, p.d0.x, p.d0.y, p.d0.z, p.d1.x, p.d1.y, p.d1.z,
+                             p.d2.x, p.d2.y, p.d2.z, 0.f, 0.f, 0.f};
+        std::memcpy(o, v, sizeof v);
+    }
+    return RTC_OK;
+}
+int rtc_scene_nodes(const rtc_scene* s, float* aabb, uint32_t* links) {
+    if (!s || !aabb || !links) return fail(RTC_ERR_ARG, "null argument");
+    for (size_t i = 0; i < s->host.nodes.size(); ++i) {
+        const RefNode& n = s->host.nodes[i];
+        const float b[6] = {n.box.mn.x, n.box.mn.y, n.box.mn.z, n.box.mx.x, n.box.mx.y, n.box.mx.z};
+        std::memcpy(aabb + 6 * i, b, sizeof b);
+        links[4 * i] = n.left; links[4 * i + 1] = n.right; links[4 * i + 2] = n.first; links[4 * i + 3] = n.count;
+    }
+    return RTC_OK;
+}
+uint32_t rtc_scene_root(const rtc_scene* s) { return s ? s->host.root : 0; }
+void rtc_set_traversal(rtc_scene* s, int mode) { if (s) s->traversal = mode == RTC_TRAVERSAL_REFTREE ? 1 : 0; }
+int rtc_set_batch_paths(rtc_scene* s, uint64_t paths) {
+    if (!s) return fail(RTC_ERR_ARG, "null scene");
+    s->batch_paths = paths ? paths : kDefaultBatchPaths;
+    if (s->batch_paths > (1ull << 28)) s->batch_paths = 1ull << 28;
+    return RTC_OK;
+}
+
+// ------------------------------------------------------------------ probes (host buffers)
+int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, int32_t* id, float* t, float* normal,
+                  int32_t* interior, int mode) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (n < 0 || !o || !d || !id || !t || !normal || !interior) return fail(RTC_ERR_ARG, "bad argument");
+    if (n == 0) return RTC_OK;
+    Staged st;
+    float* od = st.in(o, 3 * (size_t)n); NEED(od);
+    float* dd = st.in(d, 3 * (size_t)n); NEED(dd);
+    int32_t* idd = st.out<int32_t>((size_t)n); NEED(idd);
+    float* td = st.out<float>((size_t)n); NEED(td);
+    float* nd = st.out<float>(3 * (size_t)n); NEED(nd);
+    int32_t* ind = st.out<int32_t>((size_t)n); NEED(ind);
+    LaunchCtx c{nullptr, s->sms};
+    launch_intersect_batch(c, s->dev(), n, od, dd, mode == RTC_TRAVERSAL_REFTREE ? 1 : 0, idd, td, nd, ind, s->stats.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(id, idd, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(t, td, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(normal, nd, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(interior, ind, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_primitive_intersect(const rtc_scene* s, int prim, long n, const float* o, const float* d, int32_t* hit, float* t,
+                            float* normal, int32_t* interior) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (n < 0 || prim < 0 || prim >= (int)s->host.prims.size() || !o || !d || !hit || !t || !normal || !interior)
+        return fail(RTC_ERR_ARG, "bad argument");
+    if (n == 0) return RTC_OK;
+    Staged st;
+    float* od = st.in(o, 3 * (size_t)n); NEED(od);
+    float* dd = st.in(d, 3 * (size_t)n); NEED(dd);
+    int32_t* hd = st.out<int32_t>((size_t)n); NEED(hd);
+    float* td = st.out<float>((size_t)n); NEED(td);
+    float* nd = st.out<float>(3 * (size_t)n); NEED(nd);
+    int32_t* ind = st.out<int32_t>((size_t)n); NEED(ind);
+    LaunchCtx c{nullptr, s->sms};
+    launch_primitive_batch(c, s->dev(), (uint32_t)prim, n, od, dd, hd, td, nd, ind);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(hit, hd, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(t, td, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(normal, nd, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(interior, ind, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_camera_rays(const rtc_scene* s, long n, const float* xy, float* o, float* d) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (n < 0 || !xy || !o || !d) return fail(RTC_ERR_ARG, "bad argument");
+    if (n == 0) return RTC_OK;
+    Staged st;
+    float* xd = st.in(xy, 2 * (size_t)n); NEED(xd);
+    float* od = st.out<float>(3 * (size_t)n); NEED(od);
+    float* dd = st.out<float>(3 * (size_t)n); NEED(dd);
+    LaunchCtx c{nullptr, s->sms};
+    launch_camera_batch(c, s->dev(), n, xd, od, dd);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(o, od, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(d, dd, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_mix_pdf(const rtc_scene* s, long n, const float* x, const float* nrm, const float* d, float* pdf) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (n < 0 || !x || !nrm || !d || !pdf) return fail(RTC_ERR_ARG, "bad argument");
+    if (n == 0) return RTC_OK;
+    Staged st;
+    float* xd = st.in(x, 3 * (size_t)n); NEED(xd);
+    float* nd = st.in(nrm, 3 * (size_t)n); NEED(nd);
+    float* dd = st.in(d, 3 * (size_t)n); NEED(dd);
+    float* pd = st.out<float>((size_t)n); NEED(pd);
+    LaunchCtx c{nullptr, s->sms};
+    launch_pdf_batch(c, s->dev(), n, xd, nd, dd, pd);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(pdf, pd, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_mix_sample(const rtc_scene* s, long n, const float* x, const float* nrm, uint32_t seed, uint32_t sample,
+                   uint32_t bounce, float* dir) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (n < 0 || !x || !nrm || !dir) return fail(RTC_ERR_ARG, "bad argument");
+    if (n == 0) return RTC_OK;
+    Staged st;
+    float* xd = st.in(x, 3 * (size_t)n); NEED(xd);
+    float* nd = st.in(nrm, 3 * (size_t)n); NEED(nd);
+    float* dd = st.out<float>(3 * (size_t)n); NEED(dd);
+    LaunchCtx c{nullptr, s->sms};
+    launch_sample_batch(c, s->dev(), n, xd, nd, seed, sample, bounce, dd);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(dir, dd, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_tonemap_u8(const rtc_scene* s, long npix, const float* rgb, uint8_t* out) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (npix < 0 || !rgb || !out) return fail(RTC_ERR_ARG, "bad argument");
+    if (npix == 0) return RTC_OK;
+    Staged st;
+    float* rd = st.in(rgb, 3 * (size_t)npix); NEED(rd);
+    uint8_t* od = st.out<uint8_t>(3 * (size_t)npix); NEED(od);
+    LaunchCtx c{nullptr, s->sms};
+    launch_tonemap(c, rd, (uint32_t)(3 * npix), od);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, od, 3 * (size_t)npix, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+
+// ------------------------------------------------------------------ render
+int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t sample_count, float* accum_dev,
+                          void* stream) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!accum_dev) return fail(RTC_ERR_ARG, "null accumulation buffer");
+    const uint64_t npix = (uint64_t)s->host.cam.width * s->host.cam.height;
+    const uint64_t total = npix * sample_count;
+    if (total == 0) return RTC_OK;
+    const uint32_t depth = s->host.ray_depth;
+    const uint64_t cap = total < s->batch_paths ? total : s->batch_paths;
+    if ((rc = ensure_wavefront(s, cap))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    LaunchCtx c{st, s->sms};
+    DevScene S = s->dev();
+    HitSoA H{s->hit_tn.p, s->hit_id.p};
+    for (uint64_t first = 0; first < total; first += cap) {
+        uint32_t count = (uint32_t)((total - first) < cap ? (total - first) : cap);
+        CU(cudaMemsetAsync(s->queue.p, 0, kMaxDepthSlots * sizeof(uint32_t), st));
+        PathSoA cur{s->path[0][0].p, s->path[0][1].p, s->path[0][2].p, s->path[0][3].p};
+        PathSoA nxt{s->path[1][0].p, s->path[1][1].p, s->path[1][2].p, s->path[1][3].p};
+        s->span_begin(0, st);
+        launch_generate(c, S, cur, s->queue.p, first, count, seed, sample_begin);
+        s->span_end(st);
+        s->launches++;
+        for (uint32_t b = 1; b <= depth; ++b) {
+            s->span_begin(1, st);
+            launch_extend(c, S, cur, H, s->queue.p + (b - 1), count, s->traversal, s->count_visits, s->stats.p);
+            s->span_end(st);
+            s->span_begin(2, st);
+            launch_shade(c, S, cur, H, nxt, s->queue.p + (b - 1), s->queue.p + b, count, accum_dev, b, seed);
+            s->span_end(st);
+            s->launches += 2;
+            PathSoA tmp = cur; cur = nxt; nxt = tmp;
+        }
+        launch_tally(c, s->queue.p, depth, s->stats.p);
+        s->launches++;
+    }
+    CU(cudaGetLastError());
+    return RTC_OK;
+}
+int rtc_render_counters(rtc_scene* s, void* stream, uint64_t out[8]) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!out) return fail(RTC_ERR_ARG, "null argument");
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long h[8];
+    CU(cudaMemcpy(h, s->stats.p, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out[i] = h[i];
+    out[2] = s->launches;
+    return RTC_OK;
+}
+int rtc_render_reset_counters(rtc_scene* s) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    CU(cudaMemset(s->stats.p, 0, 8 * sizeof(unsigned long long)));
+    s->launches = 0;
+    return RTC_OK;
+}
+int rtc_render_resolve(rtc_scene* s, const float* accum_dev, uint32_t total_samples, uint8_t* rgb_dev, void* stream) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!accum_dev || !rgb_dev || total_samples == 0) return fail(RTC_ERR_ARG, "bad argument");
+    LaunchCtx c{(cudaStream_t)stream, s->sms};
+    uint32_t nvalues = 3u * s->host.cam.width * s->host.cam.height;
+    launch_resolve(c, accum_dev, 1.f / (float)total_samples, nvalues, rgb_dev);  // 1.f / samples * sum, src/scene.cpp:201
+    s->launches++;
+    CU(cudaGetLastError());
+    return RTC_OK;
+}
+int rtc_render_sum(rtc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t sample_count, float* sum_host) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!sum_host) return fail(RTC_ERR_ARG, "null argument");
+    size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    CU(s->accum.ensure(nvalues));
+    CU(cudaMemset(s->accum.p, 0, nvalues * sizeof(float)));
+    if ((rc = rtc_render_accumulate(s, seed, sample_begin, sample_count, s->accum.p, nullptr))) return rc;
+    CU(cudaMemcpy(sum_host, s->accum.p, nvalues * sizeof(float), cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_render_u8(rtc_scene* s, uint32_t seed, uint8_t* rgb_host) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!rgb_host) return fail(RTC_ERR_ARG, "null argument");
+    if (s->host.samples == 0) return fail(RTC_ERR_ARG, "scene has SAMPLES 0");
+    size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    CU(s->accum.ensure(nvalues));
+    CU(s->rgb.ensure(nvalues));
+    CU(cudaMemsetAsync(s->accum.p, 0, nvalues * sizeof(float), nullptr));
+    if ((rc = rtc_render_accumulate(s, seed, 0, s->host.samples, s->accum.p, nullptr))) return rc;
+    if ((rc = rtc_render_resolve(s, s->accum.p, s->host.samples, s->rgb.p, nullptr))) return rc;
+    CU(cudaMemcpy(rgb_host, s->rgb.p, nvalues, cudaMemcpyDeviceToHost));
+    return RTC_OK;
+}
+int rtc_render_ppm(rtc_scene* s, uint32_t seed, const char* out_path) {
+    if (!s || !out_path) return fail(RTC_ERR_ARG, "null argument");
+    size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    std::vector<uint8_t> img(nvalues);
+    int rc = rtc_render_u8(s, seed, img.data());
+    if (rc) return rc;
+    std::ofstream out(out_path, std::ios::binary);
+    if (!out) return fail(RTC_ERR_IO, std::string("cannot open output file ") + out_path);
+    out << "P6\n" << s->host.cam.width << " " << s->host.cam.height << "\n" << 255 << "\n";  // src/scene.cpp:206-208
+    out.write(reinterpret_cast<const char*>(img.data()), (std::streamsize)img.size());
+    if (!out) return fail(RTC_ERR_IO, std::string("write failed: ") + out_path);
+    return RTC_OK;
+}
+
+int rtc_set_profiling(rtc_scene* s, int kernel_events, int count_visits) {
+    if (!s) return fail(RTC_ERR_ARG, "null scene");
+    s->profiling = kernel_events != 0;
+    s->count_visits = count_visits != 0;
+    return RTC_OK;
+}
+int rtc_render_profile(rtc_scene* s, void* stream, double ms[4], uint64_t launches[4], int reset) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!ms || !launches) return fail(RTC_ERR_ARG, "null argument");
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    s->collect_spans();
+    for (int i = 0; i < 4; ++i) { ms[i] = s->prof_ms[i]; launches[i] = s->prof_launches[i]; }
+    if (reset) for (int i = 0; i < 4; ++i) { s->prof_ms[i] = 0; s->prof_launches[i] = 0; }
+    return RTC_OK;
+}
+
+void rtc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// main.cpp -- `raytracing_hw5 <scene.txt> <out.ppm>`: the reference's command line
+// (src/main.cpp:6-19, run.sh) on top of the C-ABI.  Extra, optional environment knobs:
+//   RTC_DEVICE=<n>   CUDA device (default 0)      RTC_SEED=<n>   RNG seed (default 0)
+//   RTC_SAMPLES / RTC_WIDTH / RTC_HEIGHT / RTC_RAY_DEPTH   override the scene file
+#include <cstdio>
+#include <cstdlib>
+
+#include "rtc_b200.h"
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+int main(int argc, const char* argv[]) {
+    if (argc < 3) {
+        std::fprintf(stderr, "usage: %s <scene.txt> <out.ppm>\n", argv[0]);
+        return 2;
+    }
+    rtc_scene* scene = rtc_scene_load(argv[1], env_int("RTC_DEVICE", 0));
+    if (!scene) {
+        std::fprintf(stderr, "raytracing_hw5: %s\n", rtc_last_error());
+        return 1;
+    }
+    rtc_scene_override(scene, env_int("RTC_WIDTH", -1), env_int("RTC_HEIGHT", -1), env_int("RTC_SAMPLES", -1),
+                       env_int("RTC_RAY_DEPTH", -1));
+    int rc = rtc_render_ppm(scene, (uint32_t)env_int("RTC_SEED", 0), argv[2]);
+    if (rc != RTC_OK) std::fprintf(stderr, "raytracing_hw5: %s\n", rtc_last_error());
+    rtc_scene_free(scene);
+    return rc == RTC_OK ? 0 : 1;
+}

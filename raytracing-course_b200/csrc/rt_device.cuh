@@ -1,0 +1,576 @@
+// rt_device.cuh -- device functions of the hw5 hot path for sm_100a: primitive intersection,
+// the two BVH traversals, the light/cosine mix distribution and the Philox streams.
+// Reference lines are cited per function (paths under /root/reference/hw5).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "device_scene.h"
+#include "scene_host.h"  // PrimType / Material / flag and IREF_* constants (plain enums)
+#include "vecmath.h"
+
+namespace rtc {
+
+#define RT_D __device__ __forceinline__
+
+constexpr float kInfF = 1e18f;      // include/bvh.h:9
+constexpr float kSceneEps = 1e-4f;  // include/scene.h:64
+constexpr float kPi = 3.14159274101257324f;  // (float)acos(-1), include/distributions.h:14
+constexpr int kRejectCap = 64;      // light sampling retries (the reference retries forever)
+constexpr int kMaxRecords = 24;     // leaf hits kept per ray before falling back to the reference tree walk
+constexpr int kIndexStack = 64;
+constexpr int kRefStack = 96;
+
+RT_D vec3 ld3(const float4& v) { return mk3(v.x, v.y, v.z); }
+RT_D float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------- Philox4x32-10
+// Counter-based streams (DESIGN.md "RNG streams"): key = (seed, 0x52544300),
+// counter = (pixel, sample, slot, block).  slot 0 = camera jitter, slot b >= 1 = the b-th hit.
+RT_D uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+struct Rng {
+    uint32_t seed, pixel, sample, slot;
+    RT_D uint4 block(uint32_t b) const {
+        return philox4x32_10(make_uint4(pixel, sample, slot, b), make_uint2(seed, 0x52544300u));
+    }
+};
+RT_D float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+RT_D void box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
+    float a = (float)((x0 >> 8) + 1u) * (1.0f / 16777216.0f);
+    float r = sqrtf(-2.0f * logf(a));
+    float th = 6.283185307179586f * u01(x1);
+    float s, c;
+    sincosf(th, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+// Distribution::SampleNormal01Vec, src/distributions.cpp:102-110
+RT_D vec3 normal_vec(uint4 b) {
+    float z0, z1, z2, z3;
+    box_muller(b.x, b.y, z0, z1);
+    box_muller(b.z, b.w, z2, z3);
+    return normalize(mk3(z0, z1, z2));
+}
+
+// ------------------------------------------------------------------------------- primitives
+struct Isect {
+    float t;
+    vec3 n;
+    int interior;
+};
+
+// Primitive::IntersectPlane, src/primitives.cpp:55-66
+RT_D bool isect_plane(vec3 o, vec3 d, vec3 n, Isect& out) {
+    float dn = dot(d, n);
+    float t = -dot(o, n) / dn;
+    if (t > 1e5f) return false;
+    if (t > 0.f) {
+        out.t = t;
+        out.interior = dn >= 0.f;
+        out.n = out.interior ? -n : n;
+        return true;
+    }
+    return false;
+}
+// Primitive::IntersectBox, src/primitives.cpp:70-117
+RT_D bool isect_box(vec3 o, vec3 d, vec3 s, Isect& out) {
+    vec3 a = (-s - o) / d, b = (s - o) / d;
+    float t1 = fmaxf(fmaxf(fminf(a.x, b.x), fminf(a.y, b.y)), fminf(a.z, b.z));
+    float t2 = fminf(fminf(fmaxf(a.x, b.x), fmaxf(a.y, b.y)), fmaxf(a.z, b.z));
+    if (t1 > t2 || t2 < 0.f) return false;
+    bool interior = t1 < 0.f;
+    float t = interior ? t2 : t1;
+    vec3 p = o + t * d;
+    vec3 nrm = p / s;
+    if (interior) nrm = -nrm;
+    float mx = fmaxf(fmaxf(fabsf(nrm.x), fabsf(nrm.y)), fabsf(nrm.z));
+    if (fabsf(nrm.x) != mx) nrm.x = 0.f;
+    if (fabsf(nrm.y) != mx) nrm.y = 0.f;
+    if (fabsf(nrm.z) != mx) nrm.z = 0.f;
+    out.t = t;
+    out.n = normalize(nrm);
+    out.interior = interior;
+    return true;
+}
+// Primitive::IntersectEllipsoid, src/primitives.cpp:120-152.  The reference evaluates the two
+// roots in double (unqualified sqrt(float) resolves to ::sqrt(double)) and rounds once; so do we.
+RT_D bool isect_ellipsoid(vec3 o, vec3 d, vec3 r, Isect& out) {
+    vec3 dr = d / r, orr = o / r;
+    float a = __fadd_rn(__fadd_rn(__fmul_rn(dr.x, dr.x), __fmul_rn(dr.y, dr.y)), __fmul_rn(dr.z, dr.z));
+    float b = __fmul_rn(2.f, __fadd_rn(__fadd_rn(__fmul_rn(orr.x, dr.x), __fmul_rn(orr.y, dr.y)), __fmul_rn(orr.z, dr.z)));
+    float c = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(orr.x, orr.x), __fmul_rn(orr.y, orr.y)), __fmul_rn(orr.z, orr.z)), -1.f);
+    float disc = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.f, a), c));
+    if (disc <= 0.f) return false;
+    double sq = sqrt((double)disc), den = (double)__fmul_rn(2.f, a);
+    float x1 = (float)(((double)(-b) - sq) / den);
+    float x2 = (float)(((double)(-b) + sq) / den);
+    if (x1 > x2) { float tmp = x1; x1 = x2; x2 = tmp; }
+    if (x2 < 0.f) return false;
+    bool interior = x1 < 0.f;
+    float t = interior ? x2 : x1;
+    vec3 p = o + t * d;
+    vec3 nrm = normalize(p / (r * r));
+    if (interior) nrm = -nrm;
+    out.t = t;
+    out.n = nrm;
+    out.interior = interior;
+    return true;
+}
+// Primitive::IntersectTriangle, src/primitives.cpp:155-174.  Faithful to the reference: the
+// plane is the one through the LOCAL ORIGIN with the triangle's normal (IntersectPlane(ray, n)),
+// and the three orientation tests then act on that point.
+RT_D bool isect_triangle(vec3 o, vec3 d, vec3 a, vec3 b, vec3 c, vec3 n, float& t_out, bool& interior) {
+    float dn = dot(d, n);
+    float t = -dot(o, n) / dn;
+    if (!(t > 0.f) || t > 1e5f) return false;
+    vec3 p = o + t * d;
+    vec3 pa = p - a;
+    if (!(dot(cross(b - a, pa), n) > 0.f)) return false;
+    if (!(dot(cross(pa, c - a), n) > 0.f)) return false;
+    if (!(dot(cross(c - b, p - b), n) > 0.f)) return false;
+    t_out = t;
+    interior = dn >= 0.f;
+    return true;
+}
+
+// Ray into the primitive's local frame: rotate(conjugate(rotator), ray + -1*pos), src/primitives.cpp:15
+RT_D void to_local(const DevScene& S, uint32_t prim, uint32_t flags, vec3& o, vec3& d) {
+    if (flags & PF_IDENT) return;
+    vec3 pos = ld3(ldg4(S.xf_pos + prim));
+    o = o - pos;
+    if (flags & PF_ROT_IDENT) return;
+    float4 q4 = ldg4(S.xf_rot + prim);
+    quat qc;
+    qc.x = -q4.x; qc.y = -q4.y; qc.z = -q4.z; qc.w = q4.w;
+    o = rotate(qc, o);
+    d = rotate(qc, d);
+}
+RT_D uint32_t prim_flags(const DevScene& S, uint32_t prim) { return __float_as_uint(__ldg(&S.xf_pos[prim].w)); }
+
+// distance-only test used during traversal (normal is recomputed once for the winner)
+RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t) {
+    uint32_t flags = prim_flags(S, prim);
+    to_local(S, prim, flags, o, d);
+    float4 g0 = ldg4(S.geo0 + prim);
+    if ((flags & PF_TYPE_MASK) == PT_TRIANGLE) {
+        float4 g1 = ldg4(S.geo1 + prim), g2 = ldg4(S.geo2 + prim);
+        bool interior;
+        return isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), mk3(g0.w, g1.w, g2.w), t, interior);
+    }
+    Isect is;
+    bool ok;
+    switch (flags & PF_TYPE_MASK) {
+        case PT_BOX: ok = isect_box(o, d, ld3(g0), is); break;
+        case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), is); break;
+        default: ok = isect_plane(o, d, ld3(g0), is); break;
+    }
+    t = is.t;
+    return ok;
+}
+// Primitive::Intersect, src/primitives.cpp:14-52 (normal back to world space, re-normalised)
+RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect& out) {
+    uint32_t flags = prim_flags(S, prim);
+    to_local(S, prim, flags, o, d);
+    float4 g0 = ldg4(S.geo0 + prim);
+    bool ok;
+    switch (flags & PF_TYPE_MASK) {
+        case PT_TRIANGLE: {
+            float4 g1 = ldg4(S.geo1 + prim), g2 = ldg4(S.geo2 + prim);
+            vec3 n = mk3(g0.w, g1.w, g2.w);
+            bool interior;
+            ok = isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), n, out.t, interior);
+            out.interior = interior;
+            out.n = interior ? -n : n;
+            break;
+        }
+        case PT_BOX: ok = isect_box(o, d, ld3(g0), out); break;
+        case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), out); break;
+        default: ok = isect_plane(o, d, ld3(g0), out); break;
+    }
+    if (!ok) return false;
+    if (!(flags & PF_ROT_IDENT)) {
+        float4 q4 = ldg4(S.xf_rot + prim);
+        quat q;
+        q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
+        out.n = rotate(q, out.n);
+    }
+    out.n = normalize(out.n);
+    return true;
+}
+
+// ------------------------------------------------------------------------------- boxes
+// AABB_t::Intersect = IntersectBox(ray - centre, half), src/bvh.cpp:89-93, with IEEE division:
+// used where the reference's own nodes decide (reference-tree walk, LCA culling).
+RT_D bool ref_box(const DevScene& S, uint32_t node, vec3 o, vec3 d, float& t_enter, bool& interior, uint32_t& left, uint32_t& right) {
+    float4 A = ldg4(S.rnodes + 2 * node), B = ldg4(S.rnodes + 2 * node + 1);
+    left = __float_as_uint(A.w);
+    right = __float_as_uint(B.w);
+    vec3 oc = o - ld3(A), s = ld3(B);
+    vec3 a = (-s - oc) / d, b = (s - oc) / d;
+    float t1 = fmaxf(fmaxf(fminf(a.x, b.x), fminf(a.y, b.y)), fminf(a.z, b.z));
+    float t2 = fminf(fminf(fmaxf(a.x, b.x), fmaxf(a.y, b.y)), fmaxf(a.z, b.z));
+    if (t1 > t2 || t2 < 0.f) return false;
+    interior = t1 < 0.f;
+    t_enter = interior ? t2 : t1;
+    return true;
+}
+
+struct BestHit {
+    float t;
+    int id;
+};
+
+// ------------------------------------------------------------------------------- reference-tree walk
+// BVH_t::Intersect_ (src/bvh.cpp:185-225) made iterative.  The recursion passes to the right
+// child the distance found in the LEFT sibling subtree (or its own closest_dist when that
+// subtree had no hit); a frame keeps that fallback plus the best hit seen before the frame was
+// opened, `cur` is the best hit since.
+RT_D BestHit trace_reftree(const DevScene& S, vec3 o, vec3 d, float cd0) {
+    struct Frame { uint32_t node; float cdf; float st; int sid; };
+    Frame stack[kRefStack];
+    int sp = 0;
+    BestHit cur{kInfF, -1};
+    if (S.nbvh == 0) return cur;
+    uint32_t v = S.root;
+    float cd = cd0;
+    for (;;) {
+        float te; bool interior; uint32_t l, r;
+        bool descend = false;
+        if (ref_box(S, v, o, d, te, interior, l, r) && !(cd < te && !interior)) {
+            if (l == 0xFFFFFFFFu) {
+                uint4 m = __ldg(S.rmeta + v);
+                for (uint32_t i = m.x; i < m.x + m.y; ++i) {
+                    float t;
+                    if (prim_hit_t(S, i, o, d, t) && t < cur.t) { cur.t = t; cur.id = (int)i; }
+                }
+            } else if (sp < kRefStack) {
+                stack[sp].node = r; stack[sp].cdf = cd; stack[sp].st = cur.t; stack[sp].sid = cur.id;
+                ++sp;
+                cur.t = kInfF; cur.id = -1;
+                v = l;
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        if (sp == 0) break;
+        --sp;
+        Frame f = stack[sp];
+        cd = (cur.id != -1) ? cur.t : f.cdf;
+        if (!(cur.t < f.st)) { cur.t = f.st; cur.id = f.sid; }
+        v = f.node;
+    }
+    return cur;
+}
+
+// ------------------------------------------------------------------------------- index traversal
+// Lowest common ancestor in the reference tree of the leaves starting at primitive a < b:
+// the shallowest inner node whose cut position lies in (a, b].
+RT_D uint32_t ref_lca(const DevScene& S, uint32_t a, uint32_t b) {
+    uint32_t lo = a + 1, len = b - a;
+    uint32_t l = 31 - __clz(len);
+    uint32_t n1 = __ldg(S.lca + (size_t)l * S.nbvh + lo);
+    uint32_t n2 = __ldg(S.lca + (size_t)l * S.nbvh + (b + 1 - (1u << l)));
+    if (n1 == 0xFFFFFFFFu) return n2;
+    if (n2 == 0xFFFFFFFFu || n1 == n2) return n1;
+    uint32_t d1 = __ldg(&S.rmeta[n1].z), d2 = __ldg(&S.rmeta[n2].z);
+    return d2 < d1 ? n2 : n1;
+}
+
+struct LeafRec {
+    uint32_t key;  // first primitive of the reference leaf (its position in DFS order)
+    int id;        // closest primitive inside the leaf
+    float t;       // its distance
+    float tcull;   // leaf box entry distance, -inf when the origin is inside the box
+};
+
+// Replays BVH_t::Intersect_ on the k leaves (sorted by key) that actually produced a hit.
+// Leaves without a hit, and subtrees without such leaves, return id = -1 in the reference and
+// influence nothing; along a chain of single-child steps closest_dist does not change and the
+// boxes shrink, so testing the skip rule at the bottom of each chain (a branching node = an LCA,
+// or the leaf) is equivalent to testing it at every node of the chain.
+RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, LeafRec* rec, int k) {
+    BestHit cur{kInfF, -1};
+    if (k == 0) return cur;
+    if (k == 1) {
+        if (!(cd0 < rec[0].tcull)) { cur.t = rec[0].t; cur.id = rec[0].id; }
+        return cur;
+    }
+    for (int i = 1; i < k; ++i) {  // insertion sort by key
+        LeafRec x = rec[i];
+        int j = i - 1;
+        while (j >= 0 && rec[j].key > x.key) { rec[j + 1] = rec[j]; --j; }
+        rec[j + 1] = x;
+    }
+    struct Frame { int m, j; float cdf; float st; int sid; };
+    Frame stack[kMaxRecords];
+    int sp = 0, i = 0, j = k;
+    float cd = cd0;
+    for (;;) {
+        bool descend = false;
+        if (j - i == 1) {
+            if (!(cd < rec[i].tcull) && rec[i].t < cur.t) { cur.t = rec[i].t; cur.id = rec[i].id; }
+        } else {
+            uint32_t u = ref_lca(S, rec[i].key, rec[j - 1].key);
+            float te; bool interior; uint32_t l, r;
+            if (ref_box(S, u, o, d, te, interior, l, r) && !(cd < te && !interior)) {
+                uint32_t cut = __ldg(&S.rmeta[u].y);
+                int m = i + 1;
+                while (rec[m].key < cut) ++m;
+                stack[sp].m = m; stack[sp].j = j; stack[sp].cdf = cd; stack[sp].st = cur.t; stack[sp].sid = cur.id;
+                ++sp;
+                cur.t = kInfF; cur.id = -1;
+                j = m;
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        if (sp == 0) break;
+        --sp;
+        Frame f = stack[sp];
+        cd = (cur.id != -1) ? cur.t : f.cdf;
+        if (!(cur.t < f.st)) { cur.t = f.st; cur.id = f.sid; }
+        i = f.m; j = f.j;
+    }
+    return cur;
+}
+
+// All reference leaves whose AABB the ray touches, via the index BVH; primitives of a touched
+// leaf are tested at once and only leaves with a hit are recorded.  Returns false when more
+// than kMaxRecords leaves produced hits (caller falls back to trace_reftree).
+RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int& k, uint32_t* visits, uint32_t* tests) {
+    k = 0;
+    if (S.iroot == IREF_NONE) return true;
+    vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    vec3 oi = o * inv;
+    uint32_t stack[kIndexStack];
+    int sp = 0;
+    uint32_t ref = S.iroot;
+    float ref_tc = -kInfF;
+    if (ref & IREF_LEAF) {
+        // a single leaf: its box is the reference root box
+        float te; bool interior; uint32_t l, r;
+        if (!ref_box(S, S.root, o, d, te, interior, l, r)) return true;
+        ref_tc = interior ? -kInfF : te;
+    }
+    for (;;) {
+        if (ref & IREF_LEAF) {
+            uint32_t first = ref & 0xFFFFFFu, count = ((ref >> 24) & 0x7Fu) + 1;
+            float bt = kInfF; int bid = -1;
+            for (uint32_t p = first; p < first + count; ++p) {
+                float t;
+                if (prim_hit_t(S, p, o, d, t) && t < bt) { bt = t; bid = (int)p; }
+            }
+            if (tests) *tests += count;
+            if (bid >= 0) {
+                if (k == kMaxRecords) return false;
+                rec[k].key = first; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc;
+                ++k;
+            }
+            if (sp == 0) break;
+            sp -= 2;
+            ref = stack[sp];
+            ref_tc = __uint_as_float(stack[sp + 1]);
+            continue;
+        }
+        if (visits) ++*visits;
+        const float4* nd = S.inodes + 4 * (size_t)ref;
+        float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
+        float lx1 = fmaf(n0.x, inv.x, -oi.x), lx2 = fmaf(n0.w, inv.x, -oi.x);
+        float ly1 = fmaf(n0.y, inv.y, -oi.y), ly2 = fmaf(n1.x, inv.y, -oi.y);
+        float lz1 = fmaf(n0.z, inv.z, -oi.z), lz2 = fmaf(n1.y, inv.z, -oi.z);
+        float lt1 = fmaxf(fmaxf(fminf(lx1, lx2), fminf(ly1, ly2)), fminf(lz1, lz2));
+        float lt2 = fminf(fminf(fmaxf(lx1, lx2), fmaxf(ly1, ly2)), fmaxf(lz1, lz2));
+        float rx1 = fmaf(n1.z, inv.x, -oi.x), rx2 = fmaf(n2.y, inv.x, -oi.x);
+        float ry1 = fmaf(n1.w, inv.y, -oi.y), ry2 = fmaf(n2.z, inv.y, -oi.y);
+        float rz1 = fmaf(n2.x, inv.z, -oi.z), rz2 = fmaf(n2.w, inv.z, -oi.z);
+        float rt1 = fmaxf(fmaxf(fminf(rx1, rx2), fminf(ry1, ry2)), fminf(rz1, rz2));
+        float rt2 = fminf(fminf(fmaxf(rx1, rx2), fmaxf(ry1, ry2)), fmaxf(rz1, rz2));
+        bool hl = lt1 <= lt2 && lt2 >= 0.f, hr = rt1 <= rt2 && rt2 >= 0.f;
+        uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
+        float ltc = lt1 < 0.f ? -kInfF : lt1, rtc = rt1 < 0.f ? -kInfF : rt1;
+        if (hl && hr) {
+            if (sp + 2 > kIndexStack) return false;
+            stack[sp] = rref; stack[sp + 1] = __float_as_uint(rtc);
+            sp += 2;
+            ref = lref; ref_tc = ltc;
+        } else if (hl) { ref = lref; ref_tc = ltc; }
+        else if (hr) { ref = rref; ref_tc = rtc; }
+        else {
+            if (sp == 0) break;
+            sp -= 2;
+            ref = stack[sp];
+            ref_tc = __uint_as_float(stack[sp + 1]);
+        }
+    }
+    return true;
+}
+
+struct SceneHit {
+    int id;  // -1 = miss
+    float t;
+    vec3 n;
+    int interior;
+};
+
+// Scene::RayIntersection, src/scene.cpp:46-77
+template <int MODE>
+RT_D SceneHit scene_intersect(const DevScene& S, vec3 o, vec3 d, uint32_t* visits, uint32_t* tests, uint32_t* fallbacks) {
+    SceneHit h;
+    h.id = -1; h.t = 0.f; h.n = mk3(0, 0, 0); h.interior = 0;
+    float closest = kInfF;
+    for (uint32_t p = S.nbvh; p < S.nprims; ++p) {  // planes are stored last
+        float t;
+        if (prim_hit_t(S, p, o, d, t) && t < closest) { closest = t; h.id = (int)p; }
+    }
+    BestHit b;
+    if (MODE == 1) {
+        b = trace_reftree(S, o, d, closest);
+    } else {
+        LeafRec rec[kMaxRecords];
+        int k;
+        if (collect_leaf_hits(S, o, d, rec, k, visits, tests)) b = replay_reference(S, o, d, closest, rec, k);
+        else {
+            if (fallbacks) ++*fallbacks;
+            b = trace_reftree(S, o, d, closest);
+        }
+    }
+    if (b.id != -1 && b.t < closest) h.id = b.id;
+    if (h.id >= 0) {
+        Isect is;
+        prim_intersect(S, (uint32_t)h.id, o, d, is);
+        h.t = is.t; h.n = is.n; h.interior = is.interior;
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------------------- distributions
+// Distribution::SampleCosine, src/distributions.cpp:144-159
+RT_D vec3 sample_cosine(const Rng& g, vec3 n) {
+    vec3 dir = normal_vec(g.block(1)) + n;
+    if (dot(dir, n) <= 1e-8f) return n;
+    if (length(dir) <= 1e-4f) return n;
+    return normalize(dir);
+}
+// Distribution::SampleBox, src/distributions.cpp:227-269
+RT_D vec3 sample_box(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
+    vec3 s = ld3(ldg4(S.geo0 + prim));
+    vec3 pos = ld3(ldg4(S.xf_pos + prim));
+    float4 q4 = ldg4(S.xf_rot + prim);
+    quat q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
+    float wx = s.x * s.x, wy = s.y * s.y, wz = s.z * s.z;
+    vec3 smp = mk3(0, 0, 0);
+    for (int j = 0; j < kRejectCap; ++j) {
+        uint4 A = g.block(2 + 2 * j), B = g.block(3 + 2 * j);
+        float u = u01(A.x);
+        float side = u01(A.y) <= 0.5f ? 1.f : -1.f;
+        u *= wx + wy + wz;
+        float c1 = 2.f * u01(A.z) - 1.f, c2 = 2.f * u01(A.w) - 1.f, c3 = 2.f * u01(B.x) - 1.f;
+        vec3 pnt = mk3(c1 * s.x, c2 * s.y, c3 * s.z);
+        if (u < wx) pnt.x = side * s.x;
+        else if (u < wx + wy) pnt.y = side * s.y;
+        else pnt.z = side * s.z;
+        vec3 on_box = rotate(q, pnt) + pos;
+        smp = normalize(on_box - x);
+        float t;
+        if (prim_hit_t(S, prim, x, smp, t)) break;
+    }
+    return smp;
+}
+// Distribution::SampleEllipsoid, src/distributions.cpp:318-338
+RT_D vec3 sample_ellipsoid(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
+    vec3 r = ld3(ldg4(S.geo0 + prim));
+    vec3 pos = ld3(ldg4(S.xf_pos + prim));
+    float4 q4 = ldg4(S.xf_rot + prim);
+    quat q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
+    vec3 smp = mk3(0, 0, 0);
+    for (int j = 0; j < kRejectCap; ++j) {
+        vec3 k = normal_vec(g.block(2 + 2 * j));
+        vec3 on = rotate(q, r * k) + pos;
+        smp = normalize(on - x);
+        float t;
+        if (prim_hit_t(S, prim, x, smp, t)) break;
+    }
+    return smp;
+}
+// Distribution::SampleMix, src/distributions.cpp:385-399
+RT_D vec3 mix_sample(const DevScene& S, const Rng& g, vec3 x, vec3 n) {
+    uint4 b0 = g.block(0);
+    float flip = u01(b0.x);
+    if (S.nlights == 0 || flip <= 0.5f) return sample_cosine(g, n);
+    float fid = u01(b0.y);
+    uint32_t id = (uint32_t)floorf(fid * (float)S.nlights);
+    uint32_t prim = (uint32_t)__ldg(S.lights + id);
+    if ((prim_flags(S, prim) & PF_TYPE_MASK) == PT_BOX) return sample_box(S, prim, g, x);
+    return sample_ellipsoid(S, prim, g, x);
+}
+// PdfPointBox / PdfPointEllipsoid, src/distributions.cpp:271-287, 340-347
+RT_D float pdf_point(const DevScene& S, uint32_t prim, bool is_box, float dist2, vec3 y, vec3 nrm, vec3 d) {
+    vec3 r = ld3(ldg4(S.geo0 + prim));
+    float p_y;
+    if (is_box) {
+        p_y = 1.f / (8.f * (r.x * r.x + r.y * r.y + r.z * r.z));
+    } else {
+        vec3 pos = ld3(ldg4(S.xf_pos + prim));
+        float4 q4 = ldg4(S.xf_rot + prim);
+        quat qc; qc.x = -q4.x; qc.y = -q4.y; qc.z = -q4.z; qc.w = q4.w;
+        vec3 n = rotate(qc, y - pos) / r;
+        p_y = 1.f / (4.f * kPi * length(mk3(n.x * r.y * r.z, r.x * n.y * r.z, r.x * r.y * n.z)));
+    }
+    return p_y * dist2 / fabsf(dot(d, nrm));
+}
+// PdfBox / PdfEllipsoid + GetPointsForPdf, src/distributions.cpp:170-198, 289-312, 349-372
+RT_D float pdf_light(const DevScene& S, uint32_t prim, vec3 x, vec3 d) {
+    bool is_box = (prim_flags(S, prim) & PF_TYPE_MASK) == PT_BOX;
+    Isect i1;
+    if (!prim_intersect(S, prim, x, d, i1)) return 1e-9f;
+    if (i1.t <= 1e-8f) return 1e-9f;
+    vec3 p1 = x + i1.t * d;
+    vec3 v1 = p1 - x;
+    float sum = pdf_point(S, prim, is_box, dot(v1, v1), p1, i1.n, d);
+    float step = i1.t + 1e-4f;
+    Isect i2;
+    if (prim_intersect(S, prim, x + step * d, d, i2)) {
+        float t2 = i2.t + step;
+        vec3 p2 = x + t2 * d;
+        vec3 v2 = p2 - x;
+        sum += pdf_point(S, prim, is_box, dot(v2, v2), p2, i2.n, d);
+    }
+    return sum;
+}
+// Distribution::PdfMix, src/distributions.cpp:401-416
+RT_D float mix_pdf(const DevScene& S, vec3 x, vec3 n, vec3 d) {
+    float sum = fmaxf(0.f, 1.f / kPi * dot(d, n));
+    if (S.nlights > 0) {
+        float prim_sum = 0.f;
+        for (uint32_t i = 0; i < S.nlights; ++i) prim_sum += pdf_light(S, (uint32_t)__ldg(S.lights + i), x, d);
+        prim_sum *= 1.f / (float)S.nlights;
+        sum = 0.5f * sum + 0.5f * prim_sum;
+    }
+    return sum;
+}
+
+// Camera::GetToRay, src/scene.cpp:180-187, without FMA contraction (bit-exact with the reference)
+RT_D void camera_ray(const DevScene& S, float x, float y, vec3& o, vec3& d) {
+    float nx = __fmul_rn(__fadd_rn(__fdiv_rn(__fmul_rn(2.f, x), (float)S.width), -1.f), S.tan_fov_x);
+    float ny = __fmul_rn(__fmul_rn(-1.f, __fadd_rn(__fdiv_rn(__fmul_rn(2.f, y), (float)S.height), -1.f)), S.tan_fov_y);
+    o = mk3(S.cam_pos.x, S.cam_pos.y, S.cam_pos.z);
+    d.x = __fadd_rn(__fadd_rn(__fmul_rn(nx, S.cam_right.x), __fmul_rn(ny, S.cam_up.x)), __fmul_rn(1.f, S.cam_forward.x));
+    d.y = __fadd_rn(__fadd_rn(__fmul_rn(nx, S.cam_right.y), __fmul_rn(ny, S.cam_up.y)), __fmul_rn(1.f, S.cam_forward.y));
+    d.z = __fadd_rn(__fadd_rn(__fmul_rn(nx, S.cam_right.z), __fmul_rn(ny, S.cam_up.z)), __fmul_rn(1.f, S.cam_forward.z));
+}
+
+// GetReflection, src/scene.cpp:79-81
+RT_D vec3 reflect_dir(vec3 n, vec3 dir) { return dir - (2.0f * n) * dot(n, dir); }
+
+}  // namespace rtc

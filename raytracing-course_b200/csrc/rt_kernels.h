@@ -1,0 +1,33 @@
+// rt_kernels.h -- host-callable launchers of the kernels in rt_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_scene.h"
+
+namespace rtc {
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int sms;  // multiprocessor count of the device (grid sizing)
+};
+
+void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, uint32_t* q, uint64_t first_path, uint32_t count,
+                     uint32_t seed, uint32_t sample_begin);
+void launch_extend(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
+                   int mode, bool count_visits, unsigned long long* stats);
+void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, const uint32_t* qin, uint32_t* qout,
+                  uint32_t max_count, float* accum, uint32_t bounce, uint32_t seed);
+void launch_tally(const LaunchCtx& c, const uint32_t* q, uint32_t ray_depth, unsigned long long* stats);
+void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out);
+void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out);
+void launch_intersect_batch(const LaunchCtx& c, const DevScene& S, long n, const float* o, const float* d, int mode, int32_t* id,
+                            float* t, float* nrm, int32_t* interior, unsigned long long* stats);
+void launch_primitive_batch(const LaunchCtx& c, const DevScene& S, uint32_t prim, long n, const float* o, const float* d,
+                            int32_t* hit, float* t, float* nrm, int32_t* interior);
+void launch_camera_batch(const LaunchCtx& c, const DevScene& S, long n, const float* xy, float* o, float* d);
+void launch_pdf_batch(const LaunchCtx& c, const DevScene& S, long n, const float* x, const float* nr, const float* d, float* pdf);
+void launch_sample_batch(const LaunchCtx& c, const DevScene& S, long n, const float* x, const float* nr, uint32_t seed,
+                         uint32_t sample, uint32_t bounce, float* dir);
+
+}  // namespace rtc

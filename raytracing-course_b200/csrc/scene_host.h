@@ -1,0 +1,101 @@
+// scene_host.h -- host side of the hw5 path: scene description, the reference-order SAH BVH,
+// the index BVH built on top of it, and the flattened arrays that are uploaded to HBM.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "vecmath.h"
+
+namespace rtc {
+
+// PRIMITIVE_TYPE / MATERIAL values follow include/primitives.h:13-18 and include/materials.h
+enum PrimType : int { PT_PLANE = 1, PT_BOX = 2, PT_ELLIPSOID = 4, PT_TRIANGLE = 8 };
+enum Material : int { MAT_DIFFUSE = 0, MAT_METALLIC = 1, MAT_DIELECTRIC = 2 };
+
+// per-primitive flag bits stored next to the type on the device
+enum PrimFlags : int {
+    PF_TYPE_MASK = 0xF,
+    PF_IDENT = 1 << 4,     // pos == 0 and rot == identity: world space == local space (dragon triangles)
+    PF_ROT_IDENT = 1 << 5  // rot == identity (pos may be non-zero)
+};
+
+struct Primitive {
+    int type = 0;
+    int material = MAT_DIFFUSE;
+    int orig = -1;  // index in file order
+    vec3 col{0, 0, 0}, emission{0, 0, 0}, pos{0, 0, 0};
+    quat rot{0, 0, 0, 1};
+    float ior = 0.f;
+    vec3 d0{0, 0, 0}, d1{0, 0, 0}, d2{0, 0, 0};  // plane n | box s | ellipsoid r | triangle a,b,c
+};
+
+struct Aabb {
+    vec3 mn, mx;
+};
+
+// BVH_t::nodes entry (include/bvh.h:30-36)
+struct RefNode {
+    Aabb box;
+    uint32_t left, right, first, count;
+};
+
+struct Camera {
+    vec3 pos{0, 0, 0}, right{0, 0, 0}, up{0, 0, 0}, forward{0, 0, 0};
+    float fov_x = 0.f;
+    unsigned width = 0, height = 0;
+};
+
+struct f4 {
+    float x, y, z, w;
+};
+struct u4 {
+    uint32_t x, y, z, w;
+};
+
+// Everything the device needs, as flat arrays (see DESIGN.md "Data layout in HBM").
+struct FlatScene {
+    // per primitive, final order
+    std::vector<f4> geo0, geo1, geo2;  // triangle: (a,n.x) (b,n.y) (c,n.z); others: (d0,0) 0 0
+    std::vector<f4> xf_pos;            // (pos.xyz, bits(type|flags))
+    std::vector<f4> xf_rot;            // quaternion xyzw
+    std::vector<f4> mat0, mat1;        // (col.rgb, bits(material)) (emission.rgb, ior)
+    // index BVH (binary, both child boxes in the node): 4 x f4 per node
+    std::vector<f4> inodes;
+    uint32_t iroot = 0;  // child reference of the root (may be a leaf reference)
+    // reference BVH: 2 x f4 per node (centre.xyz, bits(left)) (half.xyz, bits(right)) + meta
+    std::vector<f4> rnodes;
+    std::vector<u4> rmeta;  // (first, leaf ? count : cut, depth, 0)
+    // LCA range-min table over cut positions: levels x nbvh entries of node ids
+    std::vector<uint32_t> lca;
+    uint32_t lca_levels = 0;
+    std::vector<int32_t> lights;
+    uint32_t index_depth = 0, ref_depth = 0, units = 0;
+};
+
+struct HostScene {
+    Camera cam;
+    vec3 background{0, 0, 0};
+    unsigned ray_depth = 0, samples = 0;
+    std::vector<Primitive> prims;  // final order after init()
+    uint32_t nbvh = 0;             // non-plane primitives, stored first
+    std::vector<RefNode> nodes;    // reference BVH, in creation (pre-)order
+    uint32_t root = 0;
+    std::vector<int32_t> lights;   // emissive boxes / ellipsoids
+    FlatScene flat;
+
+    // Scene::Load (src/sceneload.cpp:112-176)
+    void parse(const std::string& text);
+    // Scene::InitScene (src/scene.cpp:7-40) + our index structures + flattening
+    void init();
+};
+
+// child reference encoding of the index BVH
+constexpr uint32_t IREF_LEAF = 0x80000000u;
+constexpr uint32_t IREF_NONE = 0xFFFFFFFFu;
+constexpr uint32_t IREF_MAX_LEAF_PRIMS = 128;  // 7 bits
+constexpr uint32_t IREF_MAX_PRIMS = 1u << 24;
+
+Aabb aabb_of_primitive(const Primitive& p);  // AABB_t::AABB_t(const Primitive&) src/bvh.cpp:41-87
+
+}  // namespace rtc

@@ -1,0 +1,104 @@
+"""CPU: the LOGIC of the device code (csrc/rt_device.cuh: index-BVH traversal + replay of the
+reference recursion, reference-tree walk, mix pdf / sampling), compiled for the host by
+tests/host_emul/emul.cpp, against the oracle and the reference's golden vectors.  This is a
+development aid for a container without a GPU; the real parity tests are test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, scene_path
+from orclib import f32p, i32p, u64p
+
+EMU_DIR = os.path.join(ROOT, "tests", "host_emul")
+CSRC = os.path.join(ROOT, "raytracing-course_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libemul.so")
+    srcs = [os.path.join(EMU_DIR, "emul.cpp"), os.path.join(CSRC, "rt_device.cuh"), os.path.join(CSRC, "bvh_build.cpp")]
+    objs = [os.path.join(CSRC, "build", "scene_load.o"), os.path.join(CSRC, "build", "bvh_build.o")]
+    if not all(os.path.exists(o) for o in objs):
+        pytest.skip("product objects not built")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in srcs + objs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+                               "-I" + cuda_inc, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+                               srcs[0]] + objs + ["-o", so])
+    L = C.CDLL(so)
+    L.emu_scene_load.restype = C.c_void_p
+    L.emu_scene_load.argtypes = [C.c_char_p]
+    L.emu_scene_free.argtypes = [C.c_void_p]
+    L.emu_intersect.argtypes = [C.c_void_p, C.c_long, f32p, f32p, C.c_int, i32p, f32p, f32p, i32p, u64p]
+    L.emu_mix_pdf.argtypes = [C.c_void_p, C.c_long, f32p, f32p, f32p, f32p]
+    L.emu_mix_sample.argtypes = [C.c_void_p, C.c_long, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
+    return L
+
+
+def emu_intersect(L, h, o, d, mode):
+    n = len(o)
+    pid = np.zeros(n, np.int32); t = np.zeros(n, np.float32); nrm = np.zeros((n, 3), np.float32)
+    inter = np.zeros(n, np.int32); st = np.zeros(2, np.uint64)
+    L.emu_intersect(h, n, np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32), mode, pid, t, nrm, inter, st)
+    return pid, t, nrm, inter, st
+
+
+@pytest.mark.parametrize("name", ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_traversal_matches_reference_golden(emu, name, mode):
+    g = golden(name + "_rays")
+    h = emu.emu_scene_load(scene_path(name).encode())
+    for kind, pre in (("cam", ""), ("sec", "sec_"), ("rnd", "rnd_")):
+        pid, t, nrm, inter, st = emu_intersect(emu, h, g[kind + "_o"], g[kind + "_d"], mode)
+        same = pid == g[pre + "pid"]
+        # mode 1 (reference tree walk) uses the reference's own box arithmetic: identical ids.
+        # mode 0 may flip a ray grazing a leaf box face by an ulp (DESIGN.md "Exactness").
+        assert same.mean() >= (1.0 if mode == 1 else 0.9995), (kind, (~same).sum())
+        hit = same & (pid >= 0)
+        assert np.array_equal(t[hit], g[pre + "t"][hit])
+        assert np.array_equal(nrm[hit], g[pre + "nrm"][hit])
+        assert np.array_equal(inter[hit], g[pre + "inter"][hit])
+        assert st[1] == 0  # no fallback to the slow walk on these scenes
+    emu.emu_scene_free(h)
+
+
+def test_index_traversal_visits_far_fewer_nodes(emu):
+    g = golden("practice5_dragon_10k_rays")
+    h = emu.emu_scene_load(scene_path("practice5_dragon_10k").encode())
+    *_, st = emu_intersect(emu, h, g["cam_o"], g["cam_d"], 0)
+    assert st[0] / len(g["cam_o"]) < 40  # the reference walk needs ~1100 node visits per primary ray
+    emu.emu_scene_free(h)
+
+
+def test_dragon_100k_against_oracle(emu, oracle_scenes):
+    name = "practice5_dragon_100k"
+    a = oracle_scenes(name)
+    h = emu.emu_scene_load(scene_path(name).encode())
+    import orclib
+    o, d = orclib.pixel_center_rays(a, 8)
+    want = a.intersect(o, d)
+    got = emu_intersect(emu, h, o, d, 0)
+    assert np.array_equal(got[0], want[0])
+    hit = want[0] >= 0
+    assert np.array_equal(got[1][hit], want[1][hit])
+    emu.emu_scene_free(h)
+
+
+@pytest.mark.parametrize("name", ["lights_mix", "practice5_dragon_10k"])
+def test_mix_pdf_and_sample(emu, oracle_scenes, name):
+    g = golden(name + "_rays")
+    h = emu.emu_scene_load(scene_path(name).encode())
+    x, n, d = g["pdf_x"], g["pdf_n"], g["pdf_d"]
+    pdf = np.zeros(len(x), np.float32)
+    emu.emu_mix_pdf(h, len(x), x, n, d, pdf)
+    assert np.allclose(pdf, g["pdf"], rtol=2e-6, atol=0)
+    dirs = np.zeros_like(x)
+    emu.emu_mix_sample(h, len(x), x, n, 5, 3, 2, dirs)
+    want = oracle_scenes(name).mix_sample(x, n, 5, 3, 2)
+    assert np.allclose(dirs, want, atol=2e-6)
+    emu.emu_scene_free(h)

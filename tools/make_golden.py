@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Records golden vectors from the UNMODIFIED reference (oracle/_ref/librefprobe.so, built by
+oracle/Makefile from /root/reference/hw5) into tests/golden/*.npz.
+
+Run in the development container only (the GPU box has no /root/reference; it uses the
+committed fixtures).  Each fixture stores its INPUTS (rays, points, ...) next to the
+reference's OUTPUTS, so a checker never needs the reference to evaluate it.
+
+    python tools/make_golden.py            # all fixtures
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import orclib  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SCENES = os.path.join(ROOT, "scenes")
+
+
+def unit(v):
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def rays_fixture(name, stride, seed):
+    """Primary rays through pixel centres + secondary rays leaving the primary hit points in
+    random directions + a cloud of random rays inside the scene bounds."""
+    s = orclib.Scene(orclib.ref(), os.path.join(SCENES, name + ".txt"))
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:s.height:stride, 0:s.width:stride]
+    xy = np.stack([xs.ravel() + 0.5, ys.ravel() + 0.5], 1).astype(np.float32)
+    o, d = s.camera_rays(xy)
+    pid, t, nrm, inter = s.intersect(o, d)
+    hit = pid >= 0
+    p = (o + t[:, None] * d)[hit]
+    sd = unit(rng.normal(size=p.shape))
+    so = (p + np.float32(1e-4) * sd).astype(np.float32)
+    spid, st, snrm, sinter = s.intersect(so, sd)
+    # random rays: origins in a box around the camera/scene, directions uniform
+    lo, hi = (-4.5, -4.5, -4.5), (4.5, 4.5, 14.0)
+    if name.startswith("practice5_1") or name.startswith("practice5_2") or name == "lights_mix":
+        lo, hi = (-6, 0.05, -9), (6, 5, 6)
+    ro = rng.uniform(lo, hi, size=(len(so), 3)).astype(np.float32)
+    rd = unit(rng.normal(size=ro.shape))
+    rpid, rt, rnrm, rinter = s.intersect(ro, rd)
+    # pdf of the mix distribution at the secondary origins
+    pn = nrm[hit]
+    pdf = s.mix_pdf(so, pn, sd)
+    tm, data = s.prims()
+    aabb, links, root = s.nodes()
+    np.savez_compressed(
+        os.path.join(GOLD, name + "_rays.npz"),
+        xy=xy, cam_o=o, cam_d=d, pid=pid, t=t, nrm=nrm, inter=inter,
+        sec_o=so, sec_d=sd, sec_pid=spid, sec_t=st, sec_nrm=snrm, sec_inter=sinter,
+        rnd_o=ro, rnd_d=rd, rnd_pid=rpid, rnd_t=rt, rnd_nrm=rnrm, rnd_inter=rinter,
+        pdf_x=so, pdf_n=pn, pdf_d=sd, pdf=pdf,
+        prim_type_material=tm, prim_data_crc=np.array([np.bitwise_xor.reduce(data.view(np.uint32).ravel())], np.uint32),
+        node_links_crc=np.array([np.bitwise_xor.reduce((links.ravel().astype(np.uint64) * np.arange(1, links.size + 1, dtype=np.uint64)) & np.uint64(0xFFFFFFFF))], np.uint64),
+        node_aabb_sum=aabb.astype(np.float64).sum(0), nnodes=np.array([s.nnodes]), root=np.array([root]),
+        info=np.array([s.width, s.height, s.ray_depth, s.samples, s.nprims, s.nbvh, s.nnodes, s.nlights]))
+    print(name, "rays:", len(o), "hit frac %.3f" % hit.mean(), "secondary", len(so))
+    s.close()
+
+
+def primitive_fixture():
+    """Primitive::Intersect of every primitive of lights_mix / practice5_2 for random rays aimed
+    roughly at the primitive (hits, misses, interior starts)."""
+    out = {}
+    for name in ("practice5_2", "lights_mix"):
+        s = orclib.Scene(orclib.ref(), os.path.join(SCENES, name + ".txt"))
+        tm, data = s.prims()
+        rng = np.random.default_rng(7)
+        for prim in range(s.nprims):
+            pos = data[prim, 6:9]
+            n = 2000
+            o = (pos + rng.normal(scale=1.5, size=(n, 3))).astype(np.float32)
+            o[: n // 4] = (pos + rng.normal(scale=0.2, size=(n // 4, 3))).astype(np.float32)  # many start inside
+            target = pos + rng.normal(scale=0.5, size=(n, 3))
+            d = unit(target - o)
+            d[n // 2:] *= rng.uniform(0.2, 3.0, size=(n - n // 2, 1)).astype(np.float32)  # unnormalised directions too
+            hit, t, nrm, inter = s.primitive_intersect(prim, o, d)
+            key = "%s_%d" % (name, prim)
+            out[key + "_o"] = o; out[key + "_d"] = d; out[key + "_hit"] = hit; out[key + "_t"] = t
+            out[key + "_nrm"] = nrm; out[key + "_inter"] = inter
+        s.close()
+    np.savez_compressed(os.path.join(GOLD, "primitive_intersect.npz"), **out)
+    print("primitive fixture:", len(out) // 6, "primitives")
+
+
+def tonemap_fixture():
+    s = orclib.Scene(orclib.ref(), os.path.join(SCENES, "practice5_1.txt"))
+    rng = np.random.default_rng(3)
+    x = np.concatenate([np.linspace(0, 4, 30000, dtype=np.float32), rng.exponential(0.5, 30000).astype(np.float32),
+                        np.array([0, 1e-8, 1e-3, 0.5, 1, 10, 1e6, -0.0, -1, -0.01] * 3, np.float32)])
+    x = x[: (len(x) // 3) * 3].reshape(-1, 3)
+    np.savez_compressed(os.path.join(GOLD, "tonemap.npz"), rgb=x, u8=s.tonemap_u8(x))
+    s.close()
+    print("tonemap fixture:", x.shape)
+
+
+def render_fixture(name, width, height, samples, ray_depth=-1):
+    """Reference render (its own minstd streams), linear radiance before tonemapping."""
+    s = orclib.Scene(orclib.ref(), os.path.join(SCENES, name + ".txt"))
+    s.override(width, height, samples, ray_depth)
+    img = s.ref_render_linear().reshape(height, width, 3)
+    np.savez_compressed(os.path.join(GOLD, "%s_render_%dx%d_%dspp.npz" % (name, width, height, samples)),
+                        mean=img, info=np.array([width, height, samples, s.ray_depth]))
+    print(name, "render", img.shape, "mean", img.mean(axis=(0, 1)))
+    s.close()
+
+
+def sort_fixture():
+    """std::sort / std::partition permutations on keys with many ties (what the BVH order hinges on)."""
+    rng = np.random.default_rng(11)
+    out = {}
+    L = orclib.ref().lib
+    for i, (n, kinds) in enumerate([(1, 1), (2, 1), (16, 1), (17, 1), (100, 1), (1000, 1), (9993, 1), (1000, 3), (5000, 40), (4096, 4096)]):
+        key = rng.integers(0, kinds, size=n).astype(np.float32)
+        perm = np.arange(n, dtype=np.int32)
+        L.ref_std_sort_perm(key, perm, 0, n)
+        out["sort%d_key" % i] = key; out["sort%d_perm" % i] = perm
+        pred = (rng.random(n) < 0.7).astype(np.uint8)
+        perm2 = np.arange(n, dtype=np.int32)
+        cut = L.ref_std_partition(perm2, pred, n)
+        out["part%d_pred" % i] = pred; out["part%d_perm" % i] = perm2; out["part%d_cut" % i] = np.array([cut])
+    np.savez_compressed(os.path.join(GOLD, "libstdcxx_order.npz"), **out)
+    print("sort fixture done")
+
+
+def main():
+    if not orclib.have_ref():
+        raise SystemExit("oracle/_ref/librefprobe.so missing: run `make -C oracle` where /root/reference exists")
+    os.makedirs(GOLD, exist_ok=True)
+    sort_fixture()
+    tonemap_fixture()
+    primitive_fixture()
+    rays_fixture("practice5_1", 8, 1)
+    rays_fixture("practice5_2", 8, 2)
+    rays_fixture("lights_mix", 1, 3)
+    rays_fixture("practice5_dragon_10k", 4, 4)
+    render_fixture("practice5_1", 64, 48, 256)
+    render_fixture("practice5_2", 64, 48, 1024)
+    render_fixture("lights_mix", 48, 32, 1024)
+    render_fixture("practice5_dragon_10k", 64, 64, 256)
+
+
+if __name__ == "__main__":
+    main()

@@ -268,26 +268,36 @@ def main():
     e2e_value = total_paths / (e2e_ms * 1e-3) / 1e6
 
     if rank == 0:
-        # roofline of the dominant kernel (k_extend), per launch, rank 0
+        # roofline of the dominant kernel, per launch, rank 0 (algorithmic bytes: DESIGN.md "Roofline")
         rays0 = max(cnt["rays"], 1)
-        visits_per_ray = stats["index_node_visits"] / max(stats["rays"], 1)
-        tests_per_ray = stats["prim_tests"] / max(stats["rays"], 1)
+        trav0 = max(cnt["traversed_rays"], 1)
+        visits_per_ray = stats["index_node_visits"] / max(stats["traversed_rays"], 1)
+        tests_per_ray = stats["prim_tests"] / max(stats["traversed_rays"], 1)
         planes = scene.nprims - scene.nbvh
-        bytes_per_ray = 32 + 20 + 64 * visits_per_ray + 48 * tests_per_ray + 48 * planes + 48
-        ext = prof["extend"]
-        launches = max(ext["launches"], 1)
-        per_launch_bytes = bytes_per_ray * rays0 / launches
-        per_launch_ms = ext["ms"] / launches
+        alg = {  # (bytes per unit, units processed in the timed region, kernel)
+            "traverse": (4 + 32 + 4 + 4 + 64 * visits_per_ray + 48 * tests_per_ray, trav0,
+                         "k_traverse" if args.traversal == 0 else "k_extend_reftree"),
+            "pre": (32 + 8 + 64 + 32 * planes + 4 * (trav0 / rays0), rays0, "k_pre"),
+            "shade": (64 + 4 + 48 + 32 + 64 + 12, rays0, "k_shade"),
+        }
+        top = max(alg, key=lambda k: prof[k]["ms"])
+        bytes_per_unit, units, kname = alg[top]
+        launches = max(prof[top]["launches"], 1)
+        per_launch_ms = prof[top]["ms"] / launches
+        per_launch_bytes = bytes_per_unit * units / launches
         peak, peak_src = measured_peaks()
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         kernel_ms = {k: v["ms"] / args.steps for k, v in prof.items()}
-        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_ray": bytes_per_ray, "index_node_visits_per_ray": visits_per_ray,
-                    "prim_tests_per_ray": tests_per_ray, "avg_launch_ms": per_launch_ms, "launches": launches,
-                    "share_of_step": (ext["ms"] / args.steps) / ms_per_step if ms_per_step > 0 else None,
+                    "bytes_per_unit": bytes_per_unit, "unit_name": "ray entering the BVH" if top == "traverse" else "ray",
+                    "units_per_launch": units / launches,
+                    "index_node_visits_per_traversed_ray": visits_per_ray, "prim_tests_per_traversed_ray": tests_per_ray,
+                    "traversed_fraction_of_rays": trav0 / rays0,
+                    "avg_launch_ms": per_launch_ms, "launches": launches,
+                    "share_of_step": (prof[top]["ms"] / args.steps) / ms_per_step if ms_per_step > 0 else None,
                     "kernel_ms_per_step": kernel_ms,
-                    "mrays_per_s_in_kernel": rays0 / (ext["ms"] * 1e-3) / 1e6 if ext["ms"] > 0 else None}
+                    "munits_per_s_in_kernel": units / (prof[top]["ms"] * 1e-3) / 1e6 if prof[top]["ms"] > 0 else None}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = reference_arm(args, 0)

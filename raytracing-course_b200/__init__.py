@@ -293,18 +293,18 @@ class Scene:
     def counters(self, stream=None):
         out = np.zeros(8, np.uint64)
         _check(self.lib, self.lib.rtc_render_counters(self.h, C.c_void_p(stream or 0), out))
-        keys = ["paths", "rays", "launches", "batches", "index_node_visits", "fallback_rays", "prim_tests"]
-        return dict(zip(keys, [int(v) for v in out[:7]]))
+        keys = ["paths", "rays", "launches", "batches", "index_node_visits", "fallback_rays", "prim_tests", "traversed_rays"]
+        return dict(zip(keys, [int(v) for v in out[:8]]))
 
     def set_profiling(self, kernel_events=False, count_visits=False):
         _check(self.lib, self.lib.rtc_set_profiling(self.h, int(kernel_events), int(count_visits)))
 
     def profile(self, stream=None, reset=True):
-        """Per kernel class (generate, extend, shade, other): total ms and launches."""
+        """Per kernel class (generate, traverse, shade, pre): total ms and launches."""
         ms = np.zeros(4, np.float64)
         n = np.zeros(4, np.uint64)
         _check(self.lib, self.lib.rtc_render_profile(self.h, C.c_void_p(stream or 0), ms, n, int(reset)))
-        names = ["generate", "extend", "shade", "other"]
+        names = ["generate", "traverse", "shade", "pre"]
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
 
     def reset_counters(self):

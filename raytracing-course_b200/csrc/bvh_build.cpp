@@ -169,6 +169,10 @@ struct IndexBuilder {
                 if (c < best) { best = c; best_axis = axis; best_cut = i; }
             }
         }
+        if (best_axis < 0) {  // every candidate cost was NaN/inf (degenerate boxes): split in the middle
+            best_axis = 2;
+            best_cut = lo + (hi - lo) / 2;
+        }
         if (best_axis != 2)
             std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
                 float ca = idx(units[a].centre, best_axis), cb = idx(units[b].centre, best_axis);
@@ -255,6 +259,12 @@ void HostScene::init() {
         F.mat1[i] = f4{p.emission.x, p.emission.y, p.emission.z, p.ior};
     }
     F.lights = lights;
+    for (uint32_t i = nbvh; i < n; ++i) {  // planes sit behind the BVH primitives (src/scene.cpp:17-19)
+        const Primitive& p = prims[i];
+        bool rot_ident = p.rot.x == 0.f && p.rot.y == 0.f && p.rot.z == 0.f && p.rot.w == 1.f;
+        F.planes.push_back(pack(p.d0, i));
+        F.planes.push_back(pack(p.pos, rot_ident ? 1u : 0u));
+    }
 
     // ---- reference tree: centre/half boxes (AABB_t::Intersect, src/bvh.cpp:89-93), depth, cuts
     const uint32_t nn = (uint32_t)nodes.size();

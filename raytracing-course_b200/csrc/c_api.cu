@@ -71,9 +71,11 @@ struct rtc_scene {
     DevBuf<int32_t> lights;
     // wavefront state
     DevBuf<float4> path[2][4];
-    DevBuf<float4> hit_tn;
+    DevBuf<float> hit_cd;
     DevBuf<uint32_t> hit_id;
-    DevBuf<uint32_t> queue;              // kMaxDepthSlots words
+    DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
+    DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
+    DevBuf<float4> planes;
     DevBuf<unsigned long long> stats;    // 8 words
     DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
     DevBuf<uint8_t> rgb;
@@ -84,7 +86,7 @@ struct rtc_scene {
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
-    double prof_ms[4] = {0, 0, 0, 0};      // generate, extend, shade, other
+    double prof_ms[4] = {0, 0, 0, 0};      // generate, traverse (or reference-tree extend), shade, pre
     uint64_t prof_launches[4] = {0, 0, 0, 0};
 
     cudaEvent_t get_event() {
@@ -121,7 +123,8 @@ struct rtc_scene {
         std::memset(&S, 0, sizeof S);
         S.geo0 = geo0.p; S.geo1 = geo1.p; S.geo2 = geo2.p; S.xf_pos = xf_pos.p; S.xf_rot = xf_rot.p;
         S.mat0 = mat0.p; S.mat1 = mat1.p; S.inodes = inodes.p; S.rnodes = rnodes.p; S.rmeta = rmeta.p;
-        S.lca = lca.p; S.lights = lights.p;
+        S.lca = lca.p; S.lights = lights.p; S.planes = planes.p;
+        S.nplanes = (uint32_t)(host.flat.planes.size() / 2);
         S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
         S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
         S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;
@@ -140,9 +143,9 @@ struct rtc_scene {
     }
     void release_device() {
         geo0.release(); geo1.release(); geo2.release(); xf_pos.release(); xf_rot.release(); mat0.release(); mat1.release();
-        inodes.release(); rnodes.release(); rmeta.release(); lca.release(); lights.release();
+        inodes.release(); rnodes.release(); rmeta.release(); lca.release(); lights.release(); planes.release();
         for (auto& set : path) for (auto& b : set) b.release();
-        hit_tn.release(); hit_id.release(); queue.release(); stats.release(); accum.release(); rgb.release();
+        hit_cd.release(); hit_id.release(); trav_queue.release(); queue.release(); stats.release(); accum.release(); rgb.release();
         collect_spans();
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
         event_pool.clear();
@@ -178,7 +181,8 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
     if ((rc = upload(s->rmeta, F.rmeta, bytes))) return rc;
     if ((rc = upload(s->lca, F.lca, bytes))) return rc;
     if ((rc = upload(s->lights, F.lights, bytes))) return rc;
-    CU(s->queue.ensure(kMaxDepthSlots));
+    if ((rc = upload(s->planes, F.planes, bytes))) return rc;
+    CU(s->queue.ensure(3 * kMaxDepthSlots));
     if (!s->stats.p) {
         CU(s->stats.ensure(8));
         CU(cudaMemset(s->stats.p, 0, 8 * sizeof(unsigned long long)));
@@ -260,8 +264,9 @@ struct Staged {
 
 int ensure_wavefront(rtc_scene* s, uint64_t cap) {
     for (auto& set : s->path) for (auto& b : set) CU(b.ensure(cap));
-    CU(s->hit_tn.ensure(cap));
+    CU(s->hit_cd.ensure(cap));
     CU(s->hit_id.ensure(cap));
+    CU(s->trav_queue.ensure(cap));
     return RTC_OK;
 }
 
@@ -366,6 +371,7 @@ int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, in
     if (rc) return rc;
     if (n < 0 || !o || !d || !id || !t || !normal || !interior) return fail(RTC_ERR_ARG, "bad argument");
     if (n == 0) return RTC_OK;
+    if ((uint64_t)n > (1ull << 30)) return fail(RTC_ERR_ARG, "too many rays in one call");
     Staged st;
     float* od = st.in(o, 3 * (size_t)n); NEED(od);
     float* dd = st.in(d, 3 * (size_t)n); NEED(dd);
@@ -373,8 +379,23 @@ int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, in
     float* td = st.out<float>((size_t)n); NEED(td);
     float* nd = st.out<float>(3 * (size_t)n); NEED(nd);
     int32_t* ind = st.out<int32_t>((size_t)n); NEED(ind);
+    // the same kernels as the render path: rays into the float4 queue layout, extend, read back
+    PathSoA P{st.out<float4>((size_t)n), st.out<float4>((size_t)n), nullptr, nullptr};
+    NEED(P.o); NEED(P.d);
+    HitSoA H{st.out<float>((size_t)n), st.out<uint32_t>((size_t)n)};
+    NEED(H.cd); NEED(H.id);
+    uint32_t* tq = st.out<uint32_t>((size_t)n); NEED(tq);
+    uint32_t* q = st.out<uint32_t>(4); NEED(q);
+    CU(cudaMemset(q, 0, 4 * sizeof(uint32_t)));
     LaunchCtx c{nullptr, s->sms};
-    launch_intersect_batch(c, s->dev(), n, od, dd, mode == RTC_TRAVERSAL_REFTREE ? 1 : 0, idd, td, nd, ind, s->stats.p);
+    DevScene S = s->dev();
+    launch_pack_rays(c, n, od, dd, P, q);
+    if (mode == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, P, H, q, (uint32_t)n);
+    else {
+        launch_pre(c, S, P, H, q, (uint32_t)n, tq, q + 1);
+        launch_traverse(c, S, P, H, (uint32_t)n, tq, q + 1, q + 2, false, s->stats.p);
+    }
+    launch_unpack_hits(c, S, n, P, H, idd, td, nd, ind);
     CU(cudaGetLastError());
     CU(cudaMemcpy(id, idd, (size_t)n * 4, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(t, td, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -483,10 +504,12 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     cudaStream_t st = (cudaStream_t)stream;
     LaunchCtx c{st, s->sms};
     DevScene S = s->dev();
-    HitSoA H{s->hit_tn.p, s->hit_id.p};
+    HitSoA H{s->hit_cd.p, s->hit_id.p};
+    uint32_t* tqc = s->queue.p + kMaxDepthSlots;      // rays queued for k_traverse, per bounce
+    uint32_t* cursor = s->queue.p + 2 * kMaxDepthSlots; // k_traverse work cursors, per bounce
     for (uint64_t first = 0; first < total; first += cap) {
         uint32_t count = (uint32_t)((total - first) < cap ? (total - first) : cap);
-        CU(cudaMemsetAsync(s->queue.p, 0, kMaxDepthSlots * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(s->queue.p, 0, 3 * kMaxDepthSlots * sizeof(uint32_t), st));
         PathSoA cur{s->path[0][0].p, s->path[0][1].p, s->path[0][2].p, s->path[0][3].p};
         PathSoA nxt{s->path[1][0].p, s->path[1][1].p, s->path[1][2].p, s->path[1][3].p};
         s->span_begin(0, st);
@@ -494,16 +517,27 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         s->span_end(st);
         s->launches++;
         for (uint32_t b = 1; b <= depth; ++b) {
-            s->span_begin(1, st);
-            launch_extend(c, S, cur, H, s->queue.p + (b - 1), count, s->traversal, s->count_visits, s->stats.p);
-            s->span_end(st);
+            if (s->traversal == RTC_TRAVERSAL_REFTREE) {
+                s->span_begin(1, st);
+                launch_extend_reftree(c, S, cur, H, s->queue.p + (b - 1), count);
+                s->span_end(st);
+                s->launches += 1;
+            } else {
+                s->span_begin(3, st);
+                launch_pre(c, S, cur, H, s->queue.p + (b - 1), count, s->trav_queue.p, tqc + (b - 1));
+                s->span_end(st);
+                s->span_begin(1, st);
+                launch_traverse(c, S, cur, H, count, s->trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
+                s->span_end(st);
+                s->launches += 2;
+            }
             s->span_begin(2, st);
             launch_shade(c, S, cur, H, nxt, s->queue.p + (b - 1), s->queue.p + b, count, accum_dev, b, seed);
             s->span_end(st);
-            s->launches += 2;
+            s->launches += 1;
             PathSoA tmp = cur; cur = nxt; nxt = tmp;
         }
-        launch_tally(c, s->queue.p, depth, s->stats.p);
+        launch_tally(c, s->queue.p, tqc, depth, s->stats.p);
         s->launches++;
     }
     CU(cudaGetLastError());

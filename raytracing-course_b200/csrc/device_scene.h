@@ -22,9 +22,10 @@ struct DevScene {
     const uint4* rmeta;
     const uint32_t* lca;
     const int32_t* lights;
+    const float4* planes;  // per plane: (n.xyz, bits(prim id)) (pos.xyz, bits(1 = no rotation))
 
     uint32_t nprims, nbvh, nnodes, root, iroot, lca_levels, nlights, ref_depth;
-    uint32_t width, height, ray_depth, pad0;
+    uint32_t width, height, ray_depth, nplanes;
     float3 cam_pos, cam_right, cam_up, cam_forward;
     float tan_fov_x, tan_fov_y;
     float3 bg;
@@ -38,8 +39,8 @@ struct PathSoA {
     float4* rad;    // radiance so far .rgb, bits(sample index)
 };
 struct HitSoA {
-    float4* tn;     // t, normal.xyz
-    uint32_t* id;   // 0xFFFFFFFF = miss, else primitive id | interior << 30
+    float* cd;      // distance of the closest plane (1e18 = none): closest_dist handed to the BVH
+    uint32_t* id;   // 0xFFFFFFFF = miss, else id of the closest primitive
 };
 
 constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;

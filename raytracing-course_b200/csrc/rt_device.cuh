@@ -345,9 +345,53 @@ RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, Leaf
     return cur;
 }
 
+// One index-BVH node: slab tests of both child boxes (min/max form, reciprocal direction; the
+// same expression is used at every level, so a hit child box implies hit ancestor boxes).
+// tc = box entry distance, or -inf when the origin is inside (the reference's `interior`).
+struct NodeVisit {
+    bool hl, hr;
+    uint32_t lref, rref;
+    float ltc, rtc;
+};
+RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) {
+    const float4* nd = S.inodes + 4 * (size_t)node;
+    float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
+    float lx1 = fmaf(n0.x, inv.x, -oi.x), lx2 = fmaf(n0.w, inv.x, -oi.x);
+    float ly1 = fmaf(n0.y, inv.y, -oi.y), ly2 = fmaf(n1.x, inv.y, -oi.y);
+    float lz1 = fmaf(n0.z, inv.z, -oi.z), lz2 = fmaf(n1.y, inv.z, -oi.z);
+    float lt1 = fmaxf(fmaxf(fminf(lx1, lx2), fminf(ly1, ly2)), fminf(lz1, lz2));
+    float lt2 = fminf(fminf(fmaxf(lx1, lx2), fmaxf(ly1, ly2)), fmaxf(lz1, lz2));
+    float rx1 = fmaf(n1.z, inv.x, -oi.x), rx2 = fmaf(n2.y, inv.x, -oi.x);
+    float ry1 = fmaf(n1.w, inv.y, -oi.y), ry2 = fmaf(n2.z, inv.y, -oi.y);
+    float rz1 = fmaf(n2.x, inv.z, -oi.z), rz2 = fmaf(n2.w, inv.z, -oi.z);
+    float rt1 = fmaxf(fmaxf(fminf(rx1, rx2), fminf(ry1, ry2)), fminf(rz1, rz2));
+    float rt2 = fminf(fminf(fmaxf(rx1, rx2), fmaxf(ry1, ry2)), fmaxf(rz1, rz2));
+    NodeVisit v;
+    v.hl = lt1 <= lt2 && lt2 >= 0.f;
+    v.hr = rt1 <= rt2 && rt2 >= 0.f;
+    v.lref = __float_as_uint(n3.x);
+    v.rref = __float_as_uint(n3.y);
+    v.ltc = lt1 < 0.f ? -kInfF : lt1;
+    v.rtc = rt1 < 0.f ? -kInfF : rt1;
+    return v;
+}
+// closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)
+RT_D void leaf_best(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, int& bid, uint32_t* tests) {
+    uint32_t first = ref & 0xFFFFFFu, count = ((ref >> 24) & 0x7Fu) + 1;
+    bt = kInfF;
+    bid = -1;
+    for (uint32_t p = first; p < first + count; ++p) {
+        float t;
+        if (prim_hit_t(S, p, o, d, t) && t < bt) { bt = t; bid = (int)p; }
+    }
+    if (tests) *tests += count;
+}
+
 // All reference leaves whose AABB the ray touches, via the index BVH; primitives of a touched
 // leaf are tested at once and only leaves with a hit are recorded.  Returns false when more
 // than kMaxRecords leaves produced hits (caller falls back to trace_reftree).
+// (Straight-line form; the render path runs the same steps from the persistent kernel
+// k_traverse in rt_kernels.cu.)
 RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int& k, uint32_t* visits, uint32_t* tests) {
     k = 0;
     if (S.iroot == IREF_NONE) return true;
@@ -365,16 +409,11 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
     }
     for (;;) {
         if (ref & IREF_LEAF) {
-            uint32_t first = ref & 0xFFFFFFu, count = ((ref >> 24) & 0x7Fu) + 1;
-            float bt = kInfF; int bid = -1;
-            for (uint32_t p = first; p < first + count; ++p) {
-                float t;
-                if (prim_hit_t(S, p, o, d, t) && t < bt) { bt = t; bid = (int)p; }
-            }
-            if (tests) *tests += count;
+            float bt; int bid;
+            leaf_best(S, ref, o, d, bt, bid, tests);
             if (bid >= 0) {
                 if (k == kMaxRecords) return false;
-                rec[k].key = first; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc;
+                rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc;
                 ++k;
             }
             if (sp == 0) break;
@@ -384,28 +423,14 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
             continue;
         }
         if (visits) ++*visits;
-        const float4* nd = S.inodes + 4 * (size_t)ref;
-        float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
-        float lx1 = fmaf(n0.x, inv.x, -oi.x), lx2 = fmaf(n0.w, inv.x, -oi.x);
-        float ly1 = fmaf(n0.y, inv.y, -oi.y), ly2 = fmaf(n1.x, inv.y, -oi.y);
-        float lz1 = fmaf(n0.z, inv.z, -oi.z), lz2 = fmaf(n1.y, inv.z, -oi.z);
-        float lt1 = fmaxf(fmaxf(fminf(lx1, lx2), fminf(ly1, ly2)), fminf(lz1, lz2));
-        float lt2 = fminf(fminf(fmaxf(lx1, lx2), fmaxf(ly1, ly2)), fmaxf(lz1, lz2));
-        float rx1 = fmaf(n1.z, inv.x, -oi.x), rx2 = fmaf(n2.y, inv.x, -oi.x);
-        float ry1 = fmaf(n1.w, inv.y, -oi.y), ry2 = fmaf(n2.z, inv.y, -oi.y);
-        float rz1 = fmaf(n2.x, inv.z, -oi.z), rz2 = fmaf(n2.w, inv.z, -oi.z);
-        float rt1 = fmaxf(fmaxf(fminf(rx1, rx2), fminf(ry1, ry2)), fminf(rz1, rz2));
-        float rt2 = fminf(fminf(fmaxf(rx1, rx2), fmaxf(ry1, ry2)), fmaxf(rz1, rz2));
-        bool hl = lt1 <= lt2 && lt2 >= 0.f, hr = rt1 <= rt2 && rt2 >= 0.f;
-        uint32_t lref = __float_as_uint(n3.x), rref = __float_as_uint(n3.y);
-        float ltc = lt1 < 0.f ? -kInfF : lt1, rtc = rt1 < 0.f ? -kInfF : rt1;
-        if (hl && hr) {
+        NodeVisit v = index_visit(S, ref, inv, oi);
+        if (v.hl && v.hr) {
             if (sp + 2 > kIndexStack) return false;
-            stack[sp] = rref; stack[sp + 1] = __float_as_uint(rtc);
+            stack[sp] = v.rref; stack[sp + 1] = __float_as_uint(v.rtc);
             sp += 2;
-            ref = lref; ref_tc = ltc;
-        } else if (hl) { ref = lref; ref_tc = ltc; }
-        else if (hr) { ref = rref; ref_tc = rtc; }
+            ref = v.lref; ref_tc = v.ltc;
+        } else if (v.hl) { ref = v.lref; ref_tc = v.ltc; }
+        else if (v.hr) { ref = v.rref; ref_tc = v.rtc; }
         else {
             if (sp == 0) break;
             sp -= 2;
@@ -414,6 +439,28 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
         }
     }
     return true;
+}
+
+// Closest plane (planes are stored last and are not part of the BVH), src/scene.cpp:50-66.
+// Planes without rotation use the world-space form t = -dot(o - pos, n) / dot(d, n), which is
+// what Primitive::Intersect + IntersectPlane evaluate for an identity rotator.
+RT_D void closest_plane(const DevScene& S, vec3 o, vec3 d, float& closest, int& id) {
+    closest = kInfF;
+    id = -1;
+    for (uint32_t i = 0; i < S.nplanes; ++i) {
+        float4 a = ldg4(S.planes + 2 * i), b = ldg4(S.planes + 2 * i + 1);
+        uint32_t prim = __float_as_uint(a.w);
+        float t;
+        bool ok;
+        if (__float_as_uint(b.w)) {
+            vec3 n = ld3(a);
+            t = -dot(o - ld3(b), n) / dot(d, n);
+            ok = t > 0.f && !(t > 1e5f);
+        } else {
+            ok = prim_hit_t(S, prim, o, d, t);
+        }
+        if (ok && t < closest) { closest = t; id = (int)prim; }
+    }
 }
 
 struct SceneHit {
@@ -428,11 +475,8 @@ template <int MODE>
 RT_D SceneHit scene_intersect(const DevScene& S, vec3 o, vec3 d, uint32_t* visits, uint32_t* tests, uint32_t* fallbacks) {
     SceneHit h;
     h.id = -1; h.t = 0.f; h.n = mk3(0, 0, 0); h.interior = 0;
-    float closest = kInfF;
-    for (uint32_t p = S.nbvh; p < S.nprims; ++p) {  // planes are stored last
-        float t;
-        if (prim_hit_t(S, p, o, d, t) && t < closest) { closest = t; h.id = (int)p; }
-    }
+    float closest;
+    closest_plane(S, o, d, closest, h.id);
     BestHit b;
     if (MODE == 1) {
         b = trace_reftree(S, o, d, closest);

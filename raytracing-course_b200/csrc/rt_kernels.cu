@@ -1,16 +1,26 @@
-// rt_kernels.cu -- kernels of the wavefront integrator (generate / extend / shade / resolve)
-// and the batch "probe" kernels behind rtc_intersect, rtc_mix_pdf, ... (sm_100a).
+// rt_kernels.cu -- kernels of the wavefront integrator and the batch "probe" kernels behind
+// rtc_intersect, rtc_mix_pdf, ... (sm_100a).
+//
+// One bounce of Scene::RayTrace =
+//   k_pre       uniform work per ray: closest plane + the first index-BVH node; rays that touch
+//               neither root child box are finished, the others are queued (warp-aggregated
+//               atomics) for
+//   k_traverse  persistent warps that pull rays from that queue; every lane refills itself as
+//               soon as its ray is done, so lanes do not idle behind the longest ray of a warp
+//               (the first version of this kernel ran at ~2 active lanes per instruction);
+//   k_shade     recomputes the hit of the winning primitive (normal, interior), applies the
+//               material, writes surviving paths compacted into the next queue.
 #include "rt_device.cuh"
 #include "rt_kernels.h"
 
 namespace rtc {
 
-// ------------------------------------------------------------------------------- wavefront
-// Queue header words in device memory (one set per batch, zeroed before the batch):
-//   q[0]            number of camera paths generated
-//   q[b]  (b>=1)    number of paths alive after the shading of bounce b (input of extend b+1)
-// Every kernel reads its element count from there: no host round trip between bounces.
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+constexpr uint32_t kDone = 0xFFFFFFFFu;   // traversal finished (never a valid leaf reference)
+constexpr uint32_t kChunk = 32;           // queue slots a warp reserves per atomic
+constexpr int kRefillLanes = 8;           // refill when at least this many lanes are idle
 
+// ------------------------------------------------------------------------------- generate
 // Scene::Sample's jitter + Camera::GetToRay (src/scene.cpp:189-200): one thread per path.
 // Path ids run sample-major over the image: consecutive threads = consecutive pixels of a row.
 __global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, uint32_t* q, uint64_t first_path, uint32_t count,
@@ -34,18 +44,133 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, uint32_
     if (blockIdx.x == 0 && threadIdx.x == 0) q[0] = count;
 }
 
-// Scene::RayIntersection for every queued ray.
-template <int MODE, bool STATS>
-__global__ void __launch_bounds__(128) k_extend(DevScene S, PathSoA P, HitSoA H, const uint32_t* qcount,
-                                                 unsigned long long* stats) {
+// ------------------------------------------------------------------------------- extend, step 1
+// Planes (src/scene.cpp:50-66) and the root of the index BVH.  H.cd = closest_dist handed to
+// BVH_t::Intersect, H.id = the plane hit so far.
+__global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t* tq,
+                                              uint32_t* tq_count) {
     const uint32_t count = *qcount;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rounded = (count + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool enters = false;
+        if (i < count) {
+            vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
+            float closest;
+            int id;
+            closest_plane(S, o, d, closest, id);
+            H.cd[i] = closest;
+            H.id[i] = id < 0 ? HIT_MISS : (uint32_t)id;
+            if (S.iroot != IREF_NONE) {
+                if (S.iroot & IREF_LEAF) {
+                    float te; bool interior; uint32_t l, r;
+                    enters = ref_box(S, S.root, o, d, te, interior, l, r);
+                } else {
+                    vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    NodeVisit v = index_visit(S, S.iroot, inv, o * inv);
+                    enters = v.hl || v.hr;
+                }
+            }
+        }
+        unsigned mask = __ballot_sync(kFullMask, enters);
+        if (mask) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(tq_count, (uint32_t)__popc(mask));
+            base = __shfl_sync(kFullMask, base, 0);
+            if (enters) tq[base + __popc(mask & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- extend, step 2
+// BVH_t::Intersect (src/bvh.cpp:181-225) for the queued rays: index-BVH traversal collecting the
+// reference leaves with a hit, then the replay of the reference recursion (rt_device.cuh).
+// Persistent warps; `cursor` hands out queue slots, kChunk per atomic.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
+                                                   uint32_t* cursor, unsigned long long* stats) {
+    const uint32_t total = *tq_count;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t pool_base = 0, pool_left = 0;  // warp-uniform
+    bool exhausted = false;                 // warp-uniform: the queue has no more slots for this warp
+    bool active = false, overflow = false;
+    uint32_t ray = 0, ref = kDone;
+    vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), inv = mk3(0, 0, 0), oi = mk3(0, 0, 0);
+    float cd0 = 0.f, ref_tc = 0.f;
+    int sp = 0, k = 0;
+    uint32_t stack[kIndexStack];
+    LeafRec rec[kMaxRecords];
     uint32_t visits = 0, tests = 0, fallbacks = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        float4 o4 = P.o[i], d4 = P.d[i];
-        vec3 o = ld3(o4), d = ld3(d4);
-        SceneHit h = scene_intersect<MODE>(S, o, d, STATS ? &visits : nullptr, STATS ? &tests : nullptr, &fallbacks);
-        H.tn[i] = make_float4(h.t, h.n.x, h.n.y, h.n.z);
-        H.id[i] = h.id < 0 ? HIT_MISS : ((uint32_t)h.id | (h.interior ? HIT_INTERIOR : 0u));
+
+    for (;;) {
+        unsigned idle = __ballot_sync(kFullMask, !active);
+        if (idle && (pool_left > 0 || !exhausted) && (__popc(idle) >= kRefillLanes || idle == kFullMask)) {
+            if (pool_left == 0) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, kChunk);
+                base = __shfl_sync(kFullMask, base, 0);
+                if (base >= total) exhausted = true;
+                else { pool_base = base; pool_left = min(kChunk, total - base); }
+            }
+            uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            uint32_t serve = min((uint32_t)__popc(idle), pool_left);
+            if (!active && rank < serve) {
+                ray = __ldg(tq + pool_base + rank);
+                o = ld3(P.o[ray]);
+                d = ld3(P.d[ray]);
+                cd0 = H.cd[ray];
+                inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                oi = o * inv;
+                sp = 0; k = 0; overflow = false;
+                ref = S.iroot;
+                ref_tc = -kInfF;
+                active = true;
+                if (ref & IREF_LEAF) {  // single-leaf tree: the leaf box is the reference root box
+                    float te; bool interior; uint32_t l, r;
+                    if (ref_box(S, S.root, o, d, te, interior, l, r)) ref_tc = interior ? -kInfF : te;
+                    else ref = kDone;
+                }
+            }
+            pool_base += serve;
+            pool_left -= serve;
+        }
+        if (__ballot_sync(kFullMask, active) == 0) {
+            if (exhausted && pool_left == 0) break;
+            continue;
+        }
+        if (active) {
+            // inner nodes until this lane reaches a leaf or runs out of work
+            while (!(ref & IREF_LEAF)) {
+                if (STATS) ++visits;
+                NodeVisit v = index_visit(S, ref, inv, oi);
+                if (v.hl && v.hr) {
+                    if (sp + 2 > kIndexStack) { overflow = true; ref = kDone; break; }
+                    stack[sp] = v.rref; stack[sp + 1] = __float_as_uint(v.rtc);
+                    sp += 2;
+                    ref = v.lref; ref_tc = v.ltc;
+                } else if (v.hl) { ref = v.lref; ref_tc = v.ltc; }
+                else if (v.hr) { ref = v.rref; ref_tc = v.rtc; }
+                else if (sp == 0) ref = kDone;
+                else { sp -= 2; ref = stack[sp]; ref_tc = __uint_as_float(stack[sp + 1]); }
+            }
+            if (ref != kDone) {  // one reference leaf
+                float bt; int bid;
+                leaf_best(S, ref, o, d, bt, bid, STATS ? &tests : nullptr);
+                if (bid >= 0) {
+                    if (k == kMaxRecords) overflow = true;
+                    else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc; ++k; }
+                }
+                if (overflow || sp == 0) ref = kDone;
+                else { sp -= 2; ref = stack[sp]; ref_tc = __uint_as_float(stack[sp + 1]); }
+            }
+            if (ref == kDone) {
+                BestHit b;
+                if (overflow) { b = trace_reftree(S, o, d, cd0); ++fallbacks; }
+                else b = replay_reference(S, o, d, cd0, rec, k);
+                if (b.id != -1 && b.t < cd0) H.id[ray] = (uint32_t)b.id;  // src/scene.cpp:68-74
+                active = false;
+            }
+        }
     }
     if (fallbacks) atomicAdd(stats + 5, (unsigned long long)fallbacks);
     if (STATS) {
@@ -54,6 +179,22 @@ __global__ void __launch_bounds__(128) k_extend(DevScene S, PathSoA P, HitSoA H,
     }
 }
 
+// The node-by-node twin (RTC_TRAVERSAL_REFTREE): planes + the reference's own tree, one thread per ray.
+__global__ void __launch_bounds__(128) k_extend_reftree(DevScene S, PathSoA P, HitSoA H, const uint32_t* qcount) {
+    const uint32_t count = *qcount;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
+        float closest;
+        int id;
+        closest_plane(S, o, d, closest, id);
+        BestHit b = trace_reftree(S, o, d, closest);
+        if (b.id != -1 && b.t < closest) id = b.id;
+        H.cd[i] = closest;
+        H.id[i] = id < 0 ? HIT_MISS : (uint32_t)id;
+    }
+}
+
+// ------------------------------------------------------------------------------- shade
 RT_D void deposit(float* accum, uint32_t pixel, vec3 L) {
     atomicAdd(accum + 3 * (size_t)pixel + 0, L.x);
     atomicAdd(accum + 3 * (size_t)pixel + 1, L.y);
@@ -76,16 +217,15 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, 
             float4 b4 = P.beta[i], r4 = P.rad[i];
             beta = ld3(b4); L = ld3(r4);
             pixel = __float_as_uint(b4.w); sample = __float_as_uint(r4.w);
-            uint32_t hid = H.id[i];
-            if (hid == HIT_MISS) {
+            uint32_t prim = H.id[i];
+            Isect is;
+            vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
+            if (prim == HIT_MISS || !prim_intersect(S, prim, o, d, is)) {
                 L = L + beta * mk3(S.bg.x, S.bg.y, S.bg.z);  // src/scene.cpp:92-94
             } else {
-                float4 tn = H.tn[i];
-                uint32_t prim = hid & 0xFFFFFFu;
-                bool interior = (hid & HIT_INTERIOR) != 0;
-                vec3 normal = mk3(tn.y, tn.z, tn.w);
-                vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
-                vec3 p = o + tn.x * d;
+                bool interior = is.interior != 0;
+                vec3 normal = is.n;
+                vec3 p = o + is.t * d;
                 float4 m0 = ldg4(S.mat0 + prim), m1 = ldg4(S.mat1 + prim);
                 vec3 col = ld3(m0);
                 L = L + beta * ld3(m1);
@@ -141,11 +281,11 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, 
             }
             if (!alive) deposit(accum, pixel, L);
         }
-        unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
+        unsigned mask = __ballot_sync(kFullMask, alive);
         if (mask) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(qout, (uint32_t)__popc(mask));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            base = __shfl_sync(kFullMask, base, 0);
             if (alive) {
                 uint32_t dst = base + __popc(mask & ((1u << lane) - 1u));
                 N.o[dst] = make_float4(no.x, no.y, no.z, 0.f);
@@ -157,13 +297,14 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, 
     }
 }
 
-// totals: stats[0] += paths, stats[1] += rays, stats[3] += 1 batch
-__global__ void k_tally(const uint32_t* q, uint32_t ray_depth, unsigned long long* stats) {
-    unsigned long long rays = 0;
-    for (uint32_t b = 0; b < ray_depth; ++b) rays += q[b];
+// totals: stats[0] += paths, stats[1] += rays, stats[3] += 1 batch, stats[7] += rays sent to k_traverse
+__global__ void k_tally(const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
+    unsigned long long rays = 0, queued = 0;
+    for (uint32_t b = 0; b < ray_depth; ++b) { rays += q[b]; queued += tqc[b]; }
     stats[0] += q[0];
     stats[1] += rays;
     stats[3] += 1;
+    stats[7] += queued;
 }
 
 // Scene::Render's per-pixel tail (src/scene.cpp:201, 227-228, 247): mean, AcesTonemap,
@@ -191,21 +332,25 @@ __global__ void __launch_bounds__(256) k_tonemap(const float* rgb, uint32_t nval
 }
 
 // ------------------------------------------------------------------------------- probes
-__global__ void __launch_bounds__(128) k_intersect_batch(DevScene S, long n, const float* o, const float* d, int mode,
-                                                          int32_t* id, float* t, float* nrm, int32_t* interior,
-                                                          unsigned long long* stats) {
-    uint32_t visits = 0, fallbacks = 0;
+// rtc_intersect: rays given as 3 floats each -> the float4 queue layout of the render path, and
+// back from primitive ids to (t, normal, interior) by re-intersecting the winner.
+__global__ void k_pack_rays(long n, const float* o, const float* d, PathSoA P, uint32_t* q) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        vec3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-        SceneHit h = (mode == 1) ? scene_intersect<1>(S, ro, rd, &visits, nullptr, &fallbacks) : scene_intersect<0>(S, ro, rd, &visits, nullptr, &fallbacks);
-        id[i] = h.id;
-        t[i] = h.t;
-        nrm[3 * i] = h.n.x; nrm[3 * i + 1] = h.n.y; nrm[3 * i + 2] = h.n.z;
-        interior[i] = h.interior;
+        P.o[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], 0.f);
+        P.d[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], 0.f);
     }
-    if (stats) {
-        if (visits) atomicAdd(stats + 4, (unsigned long long)visits);
-        if (fallbacks) atomicAdd(stats + 5, (unsigned long long)fallbacks);
+    if (blockIdx.x == 0 && threadIdx.x == 0) q[0] = (uint32_t)n;
+}
+__global__ void k_unpack_hits(DevScene S, long n, PathSoA P, HitSoA H, int32_t* id, float* t, float* nrm, int32_t* interior) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        uint32_t prim = H.id[i];
+        Isect is;
+        is.t = 0.f; is.n = mk3(0, 0, 0); is.interior = 0;
+        bool ok = prim != HIT_MISS && prim_intersect(S, prim, ld3(P.o[i]), ld3(P.d[i]), is);
+        id[i] = ok ? (int32_t)prim : -1;
+        t[i] = ok ? is.t : 0.f;
+        nrm[3 * i] = ok ? is.n.x : 0.f; nrm[3 * i + 1] = ok ? is.n.y : 0.f; nrm[3 * i + 2] = ok ? is.n.z : 0.f;
+        interior[i] = ok ? is.interior : 0;
     }
 }
 __global__ void k_primitive_batch(DevScene S, uint32_t prim, long n, const float* o, const float* d, int32_t* hit, float* t,
@@ -254,19 +399,34 @@ void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, uint32_t*
                      uint32_t seed, uint32_t sample_begin) {
     k_generate<<<grid_for(count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, q, first_path, count, seed, sample_begin);
 }
-void launch_extend(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
-                   int mode, bool count_visits, unsigned long long* stats) {
-    int grid = grid_for(max_count, 128, c.sms, 16);
-    if (mode == 1) k_extend<1, false><<<grid, 128, 0, c.stream>>>(S, P, H, qcount, stats);
-    else if (count_visits) k_extend<0, true><<<grid, 128, 0, c.stream>>>(S, P, H, qcount, stats);
-    else k_extend<0, false><<<grid, 128, 0, c.stream>>>(S, P, H, qcount, stats);
+void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
+                uint32_t* tq, uint32_t* tq_count) {
+    k_pre<<<grid_for(max_count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, H, qcount, tq, tq_count);
+}
+void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t max_count, const uint32_t* tq,
+                     const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats) {
+    // persistent: exactly one resident wave of 128-thread blocks
+    static int per_sm[2] = {0, 0};
+    int v = count_visits ? 1 : 0;
+    if (per_sm[v] == 0) {
+        int n = 0;
+        cudaError_t e = count_visits ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, 128, 0)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, 128, 0);
+        per_sm[v] = (e == cudaSuccess && n > 0) ? n : 4;
+    }
+    int grid = grid_for((uint64_t)max_count, 128, c.sms, per_sm[v]);
+    if (count_visits) k_traverse<true><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, stats);
+    else k_traverse<false><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, stats);
+}
+void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count) {
+    k_extend_reftree<<<grid_for(max_count, 128, c.sms, 16), 128, 0, c.stream>>>(S, P, H, qcount);
 }
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, const uint32_t* qin, uint32_t* qout,
                   uint32_t max_count, float* accum, uint32_t bounce, uint32_t seed) {
     k_shade<<<grid_for(max_count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, H, N, qin, qout, accum, bounce, seed);
 }
-void launch_tally(const LaunchCtx& c, const uint32_t* q, uint32_t ray_depth, unsigned long long* stats) {
-    k_tally<<<1, 1, 0, c.stream>>>(q, ray_depth, stats);
+void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
+    k_tally<<<1, 1, 0, c.stream>>>(q, tqc, ray_depth, stats);
 }
 void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out) {
     k_resolve<<<grid_for(nvalues, 256, c.sms, 8), 256, 0, c.stream>>>(accum, inv_samples, nvalues, out);
@@ -274,9 +434,12 @@ void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, u
 void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out) {
     k_tonemap<<<grid_for(nvalues, 256, c.sms, 8), 256, 0, c.stream>>>(rgb, nvalues, out);
 }
-void launch_intersect_batch(const LaunchCtx& c, const DevScene& S, long n, const float* o, const float* d, int mode, int32_t* id,
-                            float* t, float* nrm, int32_t* interior, unsigned long long* stats) {
-    k_intersect_batch<<<grid_for((uint64_t)n, 128, c.sms, 16), 128, 0, c.stream>>>(S, n, o, d, mode, id, t, nrm, interior, stats);
+void launch_pack_rays(const LaunchCtx& c, long n, const float* o, const float* d, PathSoA P, uint32_t* q) {
+    k_pack_rays<<<grid_for((uint64_t)n, 256, c.sms, 8), 256, 0, c.stream>>>(n, o, d, P, q);
+}
+void launch_unpack_hits(const LaunchCtx& c, const DevScene& S, long n, PathSoA P, HitSoA H, int32_t* id, float* t, float* nrm,
+                        int32_t* interior) {
+    k_unpack_hits<<<grid_for((uint64_t)n, 256, c.sms, 8), 256, 0, c.stream>>>(S, n, P, H, id, t, nrm, interior);
 }
 void launch_primitive_batch(const LaunchCtx& c, const DevScene& S, uint32_t prim, long n, const float* o, const float* d,
                             int32_t* hit, float* t, float* nrm, int32_t* interior) {

@@ -14,15 +14,21 @@ struct LaunchCtx {
 
 void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, uint32_t* q, uint64_t first_path, uint32_t count,
                      uint32_t seed, uint32_t sample_begin);
-void launch_extend(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
-                   int mode, bool count_visits, unsigned long long* stats);
+// Scene::RayIntersection for the rays of queue P (fills H): launch_pre then launch_traverse
+// (index BVH), or launch_extend_reftree alone (the reference-tree twin).
+void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
+                uint32_t* tq, uint32_t* tq_count);
+void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t max_count, const uint32_t* tq,
+                     const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats);
+void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count);
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, const uint32_t* qin, uint32_t* qout,
                   uint32_t max_count, float* accum, uint32_t bounce, uint32_t seed);
-void launch_tally(const LaunchCtx& c, const uint32_t* q, uint32_t ray_depth, unsigned long long* stats);
+void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats);
 void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out);
 void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out);
-void launch_intersect_batch(const LaunchCtx& c, const DevScene& S, long n, const float* o, const float* d, int mode, int32_t* id,
-                            float* t, float* nrm, int32_t* interior, unsigned long long* stats);
+void launch_pack_rays(const LaunchCtx& c, long n, const float* o, const float* d, PathSoA P, uint32_t* q);
+void launch_unpack_hits(const LaunchCtx& c, const DevScene& S, long n, PathSoA P, HitSoA H, int32_t* id, float* t, float* nrm,
+                        int32_t* interior);
 void launch_primitive_batch(const LaunchCtx& c, const DevScene& S, uint32_t prim, long n, const float* o, const float* d,
                             int32_t* hit, float* t, float* nrm, int32_t* interior);
 void launch_camera_batch(const LaunchCtx& c, const DevScene& S, long n, const float* xy, float* o, float* d);

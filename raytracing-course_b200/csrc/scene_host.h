@@ -69,6 +69,7 @@ struct FlatScene {
     // LCA range-min table over cut positions: levels x nbvh entries of node ids
     std::vector<uint32_t> lca;
     uint32_t lca_levels = 0;
+    std::vector<f4> planes;            // 2 x f4 per plane: (n, bits(prim id)) (pos, bits(no rotation))
     std::vector<int32_t> lights;
     uint32_t index_depth = 0, ref_depth = 0, units = 0;
 };

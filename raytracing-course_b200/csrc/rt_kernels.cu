@@ -16,9 +16,7 @@
 namespace rtc {
 
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
-constexpr uint32_t kDone = 0xFFFFFFFFu;   // traversal finished (never a valid leaf reference)
 constexpr uint32_t kChunk = 32;           // queue slots a warp reserves per atomic
-constexpr int kRefillLanes = 8;           // refill when at least this many lanes are idle
 
 // ------------------------------------------------------------------------------- generate
 // Scene::Sample's jitter + Camera::GetToRay (src/scene.cpp:189-200): one thread per path.
@@ -85,26 +83,87 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // ------------------------------------------------------------------------------- extend, step 2
 // BVH_t::Intersect (src/bvh.cpp:181-225) for the queued rays: index-BVH traversal collecting the
 // reference leaves with a hit, then the replay of the reference recursion (rt_device.cuh).
-// Persistent warps; `cursor` hands out queue slots, kChunk per atomic.
+//
+// Persistent warps with a per-warp task scheduler.  The traversal reports ALL touched leaves in
+// any order, so the three kinds of work of a ray are decoupled: VISIT one inner node (children
+// that are leaves are only noted down), test one noted LEAF, FINISH the ray (replay + store);
+// idle lanes REFILL from the queue.  Every iteration the warp votes and executes the kind most
+// lanes are ready for, which keeps lanes busy although rays need between one and several
+// hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
+constexpr int kStackWords = 64;  // per lane: inner-node stack from the bottom, noted leaves (2 words) from the top
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
                                                    uint32_t* cursor, unsigned long long* stats) {
     const uint32_t total = *tq_count;
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t pool_base = 0, pool_left = 0;  // warp-uniform
     bool exhausted = false;                 // warp-uniform: the queue has no more slots for this warp
     bool active = false, overflow = false;
-    uint32_t ray = 0, ref = kDone;
+    uint32_t ray = 0, node = kNone;
     vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), inv = mk3(0, 0, 0), oi = mk3(0, 0, 0);
-    float cd0 = 0.f, ref_tc = 0.f;
-    int sp = 0, k = 0;
-    uint32_t stack[kIndexStack];
+    float cd0 = 0.f;
+    int sp = 0, nl = 0, k = 0;
+    uint32_t stk[kStackWords];
     LeafRec rec[kMaxRecords];
     uint32_t visits = 0, tests = 0, fallbacks = 0;
 
     for (;;) {
-        unsigned idle = __ballot_sync(kFullMask, !active);
-        if (idle && (pool_left > 0 || !exhausted) && (__popc(idle) >= kRefillLanes || idle == kFullMask)) {
+        bool room = sp + 2 * nl + 4 <= kStackWords;
+        if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
+        const bool canV = active && node != kNone && room;
+        const bool canL = active && nl > 0;
+        const bool canF = active && node == kNone && nl == 0;
+        const bool canR = !active && (pool_left > 0 || !exhausted);
+        const unsigned mV = __ballot_sync(kFullMask, canV), mL = __ballot_sync(kFullMask, canL);
+        const unsigned mF = __ballot_sync(kFullMask, canF), mR = __ballot_sync(kFullMask, canR);
+        if (!(mV | mL | mF | mR)) break;
+        const int nV = __popc(mV), nL = __popc(mL), nF = __popc(mF), nR = __popc(mR);
+
+        if (nV >= nL && nV >= nF && nV >= nR) {
+            // ---- VISIT: one inner node per ready lane
+            if (canV) {
+                if (STATS) ++visits;
+                NodeVisit v = index_visit(S, node, inv, oi);
+                uint32_t next = kNone;
+                if (v.hl) {
+                    if (v.lref & IREF_LEAF) { ++nl; stk[kStackWords - 2 * nl] = v.lref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.ltc); }
+                    else next = v.lref;
+                }
+                if (v.hr) {
+                    if (v.rref & IREF_LEAF) { ++nl; stk[kStackWords - 2 * nl] = v.rref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.rtc); }
+                    else if (next == kNone) next = v.rref;
+                    else stk[sp++] = v.rref;
+                }
+                if (next == kNone && sp > 0) next = stk[--sp];
+                node = next;
+            }
+        } else if (nL >= nF && nL >= nR) {
+            // ---- LEAF: one noted reference leaf per ready lane
+            if (canL) {
+                uint32_t ref = stk[kStackWords - 2 * nl];
+                float ref_tc = __uint_as_float(stk[kStackWords - 2 * nl + 1]);
+                --nl;
+                float bt; int bid;
+                leaf_best(S, ref, o, d, bt, bid, STATS ? &tests : nullptr);
+                if (bid >= 0) {
+                    if (k == kMaxRecords) { overflow = true; node = kNone; sp = 0; nl = 0; }
+                    else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc; ++k; }
+                }
+            }
+        } else if (nF >= nR) {
+            // ---- FINISH: replay of the reference recursion, store the winner
+            if (canF) {
+                BestHit b;
+                if (overflow) { b = trace_reftree(S, o, d, cd0); ++fallbacks; }
+                else b = replay_reference(S, o, d, cd0, rec, k);
+                if (b.id != -1 && b.t < cd0) H.id[ray] = (uint32_t)b.id;  // src/scene.cpp:68-74
+                active = false;
+            }
+        } else {
+            // ---- REFILL idle lanes from the queue
             if (pool_left == 0) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(cursor, kChunk);
@@ -112,64 +171,29 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
                 if (base >= total) exhausted = true;
                 else { pool_base = base; pool_left = min(kChunk, total - base); }
             }
-            uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-            uint32_t serve = min((uint32_t)__popc(idle), pool_left);
-            if (!active && rank < serve) {
+            uint32_t rank = __popc(mR & lt_mask);
+            uint32_t serve = min((uint32_t)nR, pool_left);
+            if (canR && rank < serve) {
                 ray = __ldg(tq + pool_base + rank);
                 o = ld3(P.o[ray]);
                 d = ld3(P.d[ray]);
                 cd0 = H.cd[ray];
                 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                 oi = o * inv;
-                sp = 0; k = 0; overflow = false;
-                ref = S.iroot;
-                ref_tc = -kInfF;
+                sp = 0; nl = 0; k = 0; overflow = false;
                 active = true;
-                if (ref & IREF_LEAF) {  // single-leaf tree: the leaf box is the reference root box
+                if (S.iroot & IREF_LEAF) {  // single-leaf tree: the leaf box is the reference root box
+                    node = kNone;
                     float te; bool interior; uint32_t l, r;
-                    if (ref_box(S, S.root, o, d, te, interior, l, r)) ref_tc = interior ? -kInfF : te;
-                    else ref = kDone;
-                }
+                    if (ref_box(S, S.root, o, d, te, interior, l, r)) {
+                        nl = 1;
+                        stk[kStackWords - 2] = S.iroot;
+                        stk[kStackWords - 1] = __float_as_uint(interior ? -kInfF : te);
+                    }
+                } else node = S.iroot;
             }
             pool_base += serve;
             pool_left -= serve;
-        }
-        if (__ballot_sync(kFullMask, active) == 0) {
-            if (exhausted && pool_left == 0) break;
-            continue;
-        }
-        if (active) {
-            // inner nodes until this lane reaches a leaf or runs out of work
-            while (!(ref & IREF_LEAF)) {
-                if (STATS) ++visits;
-                NodeVisit v = index_visit(S, ref, inv, oi);
-                if (v.hl && v.hr) {
-                    if (sp + 2 > kIndexStack) { overflow = true; ref = kDone; break; }
-                    stack[sp] = v.rref; stack[sp + 1] = __float_as_uint(v.rtc);
-                    sp += 2;
-                    ref = v.lref; ref_tc = v.ltc;
-                } else if (v.hl) { ref = v.lref; ref_tc = v.ltc; }
-                else if (v.hr) { ref = v.rref; ref_tc = v.rtc; }
-                else if (sp == 0) ref = kDone;
-                else { sp -= 2; ref = stack[sp]; ref_tc = __uint_as_float(stack[sp + 1]); }
-            }
-            if (ref != kDone) {  // one reference leaf
-                float bt; int bid;
-                leaf_best(S, ref, o, d, bt, bid, STATS ? &tests : nullptr);
-                if (bid >= 0) {
-                    if (k == kMaxRecords) overflow = true;
-                    else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc; ++k; }
-                }
-                if (overflow || sp == 0) ref = kDone;
-                else { sp -= 2; ref = stack[sp]; ref_tc = __uint_as_float(stack[sp + 1]); }
-            }
-            if (ref == kDone) {
-                BestHit b;
-                if (overflow) { b = trace_reftree(S, o, d, cd0); ++fallbacks; }
-                else b = replay_reference(S, o, d, cd0, rec, k);
-                if (b.id != -1 && b.t < cd0) H.id[ray] = (uint32_t)b.id;  // src/scene.cpp:68-74
-                active = false;
-            }
         }
     }
     if (fallbacks) atomicAdd(stats + 5, (unsigned long long)fallbacks);

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
 constexpr int kStackWords = 64;  // per lane: inner-node stack from the bottom, noted leaves (2 words) from the top
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kVisitQuorum = 20;  // at least this many lanes ready to visit: skip the full vote
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
@@ -110,37 +111,50 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
     LeafRec rec[kMaxRecords];
     uint32_t visits = 0, tests = 0, fallbacks = 0;
 
+    enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
         bool room = sp + 2 * nl + 4 <= kStackWords;
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
         const bool canV = active && node != kNone && room;
-        const bool canL = active && nl > 0;
-        const bool canF = active && node == kNone && nl == 0;
-        const bool canR = !active && (pool_left > 0 || !exhausted);
-        const unsigned mV = __ballot_sync(kFullMask, canV), mL = __ballot_sync(kFullMask, canL);
-        const unsigned mF = __ballot_sync(kFullMask, canF), mR = __ballot_sync(kFullMask, canR);
-        if (!(mV | mL | mF | mR)) break;
-        const int nV = __popc(mV), nL = __popc(mL), nF = __popc(mF), nR = __popc(mR);
+        const unsigned mV = __ballot_sync(kFullMask, canV);
+        const int nV = __popc(mV);
+        int kind = kVisit;
+        bool canL = false, canF = false, canR = false;
+        unsigned mR = 0;
+        int nR = 0;
+        if (nV < kVisitQuorum) {  // full vote only when visiting would leave too many lanes idle
+            canL = active && nl > 0;
+            canF = active && node == kNone && nl == 0;
+            canR = !active && (pool_left > 0 || !exhausted);
+            const unsigned mL = __ballot_sync(kFullMask, canL), mF = __ballot_sync(kFullMask, canF);
+            mR = __ballot_sync(kFullMask, canR);
+            if (!(mV | mL | mF | mR)) break;
+            const int nL = __popc(mL), nF = __popc(mF);
+            nR = __popc(mR);
+            if (nV >= nL && nV >= nF && nV >= nR) kind = kVisit;
+            else if (nL >= nF && nL >= nR) kind = kLeaf;
+            else if (nF >= nR) kind = kFinish;
+            else kind = kRefill;
+        }
 
-        if (nV >= nL && nV >= nF && nV >= nR) {
-            // ---- VISIT: one inner node per ready lane
+        if (kind == kVisit) {
+            // ---- VISIT: one inner node per ready lane; leaf children are only noted
             if (canV) {
                 if (STATS) ++visits;
                 NodeVisit v = index_visit(S, node, inv, oi);
-                uint32_t next = kNone;
-                if (v.hl) {
-                    if (v.lref & IREF_LEAF) { ++nl; stk[kStackWords - 2 * nl] = v.lref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.ltc); }
-                    else next = v.lref;
-                }
-                if (v.hr) {
-                    if (v.rref & IREF_LEAF) { ++nl; stk[kStackWords - 2 * nl] = v.rref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.rtc); }
-                    else if (next == kNone) next = v.rref;
-                    else stk[sp++] = v.rref;
-                }
-                if (next == kNone && sp > 0) next = stk[--sp];
-                node = next;
+                const bool lleaf = (v.lref & IREF_LEAF) != 0, rleaf = (v.rref & IREF_LEAF) != 0;
+                const bool pl = v.hl && lleaf, pr = v.hr && rleaf;    // leaves to note
+                const bool il = v.hl && !lleaf, ir = v.hr && !rleaf;  // inner children to visit
+                const int spm = sp > 0 ? sp - 1 : 0;
+                const uint32_t top = stk[spm];
+                if (pl) { ++nl; stk[kStackWords - 2 * nl] = v.lref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.ltc); }
+                if (pr) { ++nl; stk[kStackWords - 2 * nl] = v.rref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.rtc); }
+                if (il && ir) { stk[sp] = v.rref; ++sp; }
+                const bool pop = !il && !ir && sp > 0;
+                node = il ? v.lref : (ir ? v.rref : (pop ? top : kNone));
+                sp = pop ? spm : sp;
             }
-        } else if (nL >= nF && nL >= nR) {
+        } else if (kind == kLeaf) {
             // ---- LEAF: one noted reference leaf per ready lane
             if (canL) {
                 uint32_t ref = stk[kStackWords - 2 * nl];
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
                     else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc; ++k; }
                 }
             }
-        } else if (nF >= nR) {
+        } else if (kind == kFinish) {
             // ---- FINISH: replay of the reference recursion, store the winner
             if (canF) {
                 BestHit b;

@@ -122,7 +122,7 @@ struct RefBuilder {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Index BVH: a plain binary SAH tree over the reference's LEAVES ("units").  Every unit keeps
+// Index BVH: a SAH tree over the reference's LEAVES ("units"), built binary and collapsed to 4-wide nodes.  Every unit keeps
 // exactly the AABB the reference stores for that leaf; traversal reports all units whose AABB
 // the ray touches (no ordering, no early out -- see the header comment).
 struct Unit {
@@ -133,7 +133,7 @@ struct Unit {
 struct IndexBuilder {
     const std::vector<Unit>& units;
     std::vector<uint32_t> order;
-    std::vector<f4>& out;  // 4 f4 per node
+    std::vector<f4>& out;  // 8 f4 per 4-wide node
     std::vector<float> rarea;
     uint32_t max_depth = 0;
 
@@ -178,15 +178,55 @@ struct IndexBuilder {
                 float ca = idx(units[a].centre, best_axis), cb = idx(units[b].centre, best_axis);
                 return ca < cb || (ca == cb && a < b);
             });
-        uint32_t me = (uint32_t)(out.size() / 4);
-        out.resize(out.size() + 4);
+        // binary node in a temporary tree; emit() collapses it to 4-wide nodes afterwards
+        uint32_t me = (uint32_t)tmp.size();
+        tmp.push_back(Bin{});
         Aabb lb = bound(lo, best_cut), rb = bound(best_cut, hi);
         uint32_t lref = build(lo, best_cut, depth + 1);
         uint32_t rref = build(best_cut, hi, depth + 1);
-        out[4 * me + 0] = f4{lb.mn.x, lb.mn.y, lb.mn.z, lb.mx.x};
-        out[4 * me + 1] = f4{lb.mx.y, lb.mx.z, rb.mn.x, rb.mn.y};
-        out[4 * me + 2] = f4{rb.mn.z, rb.mx.x, rb.mx.y, rb.mx.z};
-        out[4 * me + 3] = bits4(lref, rref, 0, 0);
+        tmp[me] = Bin{{lb, rb}, {lref, rref}};
+        return me;
+    }
+
+    struct Bin {
+        Aabb box[2];
+        uint32_t ref[2];
+    };
+    std::vector<Bin> tmp;
+    uint32_t wide_depth = 0;
+
+    // Collapses the binary tree rooted at binary node `b` into one 4-wide node: the child with the
+    // largest surface that is still an inner node is replaced by its own two children until four
+    // slots are filled.  Returns the index of the emitted node.
+    uint32_t emit(uint32_t b, uint32_t depth) {
+        wide_depth = std::max(wide_depth, depth);
+        struct Slot { Aabb box; uint32_t ref; };
+        std::vector<Slot> slots = {{tmp[b].box[0], tmp[b].ref[0]}, {tmp[b].box[1], tmp[b].ref[1]}};
+        while (slots.size() < 4) {
+            int pick = -1;
+            float area = -1.f;
+            for (size_t i = 0; i < slots.size(); ++i)
+                if (!(slots[i].ref & IREF_LEAF) && surface(slots[i].box) > area) { area = surface(slots[i].box); pick = (int)i; }
+            if (pick < 0) break;
+            const Bin& c = tmp[slots[pick].ref];
+            slots[pick] = Slot{c.box[0], c.ref[0]};
+            slots.push_back(Slot{c.box[1], c.ref[1]});
+        }
+        uint32_t me = (uint32_t)(out.size() / 8);
+        out.resize(out.size() + 8, f4{0, 0, 0, 0});
+        float v[6][4];
+        uint32_t refs[4];
+        for (int i = 0; i < 4; ++i) {
+            bool used = i < (int)slots.size();
+            // unused slot: a far-away point box and the IREF_NONE marker
+            Aabb bx = used ? slots[i].box : Aabb{{1e30f, 1e30f, 1e30f}, {1e30f, 1e30f, 1e30f}};
+            v[0][i] = bx.mn.x; v[1][i] = bx.mn.y; v[2][i] = bx.mn.z;
+            v[3][i] = bx.mx.x; v[4][i] = bx.mx.y; v[5][i] = bx.mx.z;
+            refs[i] = IREF_NONE;
+            if (used) refs[i] = (slots[i].ref & IREF_LEAF) ? slots[i].ref : emit(slots[i].ref, depth + 1);
+        }
+        for (int r = 0; r < 6; ++r) out[8 * me + r] = f4{v[r][0], v[r][1], v[r][2], v[r][3]};
+        out[8 * me + 6] = bits4(refs[0], refs[1], refs[2], refs[3]);
         return me;
     }
 };
@@ -305,8 +345,9 @@ void HostScene::init() {
         IndexBuilder ib{units, {}, F.inodes, std::vector<float>(units.size() + 1, 0.f)};
         ib.order.resize(units.size());
         std::iota(ib.order.begin(), ib.order.end(), 0u);
-        F.iroot = ib.build(0, (uint32_t)units.size(), 0);
-        F.index_depth = ib.max_depth;
+        uint32_t broot = ib.build(0, (uint32_t)units.size(), 0);
+        F.iroot = (broot & IREF_LEAF) ? broot : ib.emit(broot, 1);
+        F.index_depth = ib.wide_depth;
     }
 
     // ---- LCA table: for a cut position c (boundary between primitive c-1 and c) the inner node

@@ -15,7 +15,7 @@ struct DevScene {
     const float4* xf_rot;  // quaternion xyzw
     const float4* mat0;    // (colour, bits(material))
     const float4* mat1;    // (emission, ior)
-    // index BVH: 4 float4 per node
+    // index BVH: 8 float4 (128 B) per 4-wide node
     const float4* inodes;
     // reference BVH: 2 float4 per node + meta
     const float4* rnodes;

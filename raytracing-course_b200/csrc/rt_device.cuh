@@ -345,34 +345,35 @@ RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, Leaf
     return cur;
 }
 
-// One index-BVH node: slab tests of both child boxes (min/max form, reciprocal direction; the
-// same expression is used at every level, so a hit child box implies hit ancestor boxes).
-// tc = box entry distance, or -inf when the origin is inside (the reference's `interior`).
+// One index-BVH node = 4 child boxes in one 128-byte line (8 float4): min.x[4] min.y[4] min.z[4]
+// max.x[4] max.y[4] max.z[4] refs[4] pad.  Slab tests in min/max form with the reciprocal
+// direction; the same expression is used at every level, so a hit child box implies hit ancestor
+// boxes.  tc = box entry distance, or -inf when the origin is inside (the reference's `interior`).
 struct NodeVisit {
-    bool hl, hr;
-    uint32_t lref, rref;
-    float ltc, rtc;
+    uint32_t ref[4];
+    float tc[4];
+    bool hit[4];
 };
+RT_D void slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 inv, vec3 oi, uint32_t ref, bool& hit, float& tc) {
+    float x1 = fmaf(mnx, inv.x, -oi.x), x2 = fmaf(mxx, inv.x, -oi.x);
+    float y1 = fmaf(mny, inv.y, -oi.y), y2 = fmaf(mxy, inv.y, -oi.y);
+    float z1 = fmaf(mnz, inv.z, -oi.z), z2 = fmaf(mxz, inv.z, -oi.z);
+    float t1 = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    float t2 = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    hit = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
+    tc = t1 < 0.f ? -kInfF : t1;
+}
 RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) {
-    const float4* nd = S.inodes + 4 * (size_t)node;
-    float4 n0 = ldg4(nd), n1 = ldg4(nd + 1), n2 = ldg4(nd + 2), n3 = ldg4(nd + 3);
-    float lx1 = fmaf(n0.x, inv.x, -oi.x), lx2 = fmaf(n0.w, inv.x, -oi.x);
-    float ly1 = fmaf(n0.y, inv.y, -oi.y), ly2 = fmaf(n1.x, inv.y, -oi.y);
-    float lz1 = fmaf(n0.z, inv.z, -oi.z), lz2 = fmaf(n1.y, inv.z, -oi.z);
-    float lt1 = fmaxf(fmaxf(fminf(lx1, lx2), fminf(ly1, ly2)), fminf(lz1, lz2));
-    float lt2 = fminf(fminf(fmaxf(lx1, lx2), fmaxf(ly1, ly2)), fmaxf(lz1, lz2));
-    float rx1 = fmaf(n1.z, inv.x, -oi.x), rx2 = fmaf(n2.y, inv.x, -oi.x);
-    float ry1 = fmaf(n1.w, inv.y, -oi.y), ry2 = fmaf(n2.z, inv.y, -oi.y);
-    float rz1 = fmaf(n2.x, inv.z, -oi.z), rz2 = fmaf(n2.w, inv.z, -oi.z);
-    float rt1 = fmaxf(fmaxf(fminf(rx1, rx2), fminf(ry1, ry2)), fminf(rz1, rz2));
-    float rt2 = fminf(fminf(fmaxf(rx1, rx2), fmaxf(ry1, ry2)), fmaxf(rz1, rz2));
+    const float4* nd = S.inodes + 8 * (size_t)node;
+    float4 ax = ldg4(nd), ay = ldg4(nd + 1), az = ldg4(nd + 2), bx = ldg4(nd + 3), by = ldg4(nd + 4), bz = ldg4(nd + 5);
+    float4 rf = ldg4(nd + 6);
     NodeVisit v;
-    v.hl = lt1 <= lt2 && lt2 >= 0.f;
-    v.hr = rt1 <= rt2 && rt2 >= 0.f;
-    v.lref = __float_as_uint(n3.x);
-    v.rref = __float_as_uint(n3.y);
-    v.ltc = lt1 < 0.f ? -kInfF : lt1;
-    v.rtc = rt1 < 0.f ? -kInfF : rt1;
+    v.ref[0] = __float_as_uint(rf.x); v.ref[1] = __float_as_uint(rf.y);
+    v.ref[2] = __float_as_uint(rf.z); v.ref[3] = __float_as_uint(rf.w);
+    slab(ax.x, ay.x, az.x, bx.x, by.x, bz.x, inv, oi, v.ref[0], v.hit[0], v.tc[0]);
+    slab(ax.y, ay.y, az.y, bx.y, by.y, bz.y, inv, oi, v.ref[1], v.hit[1], v.tc[1]);
+    slab(ax.z, ay.z, az.z, bx.z, by.z, bz.z, inv, oi, v.ref[2], v.hit[2], v.tc[2]);
+    slab(ax.w, ay.w, az.w, bx.w, by.w, bz.w, inv, oi, v.ref[3], v.hit[3], v.tc[3]);
     return v;
 }
 // closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)
@@ -424,14 +425,16 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
         }
         if (visits) ++*visits;
         NodeVisit v = index_visit(S, ref, inv, oi);
-        if (v.hl && v.hr) {
+        bool have = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (!v.hit[c]) continue;
+            if (!have) { ref = v.ref[c]; ref_tc = v.tc[c]; have = true; continue; }
             if (sp + 2 > kIndexStack) return false;
-            stack[sp] = v.rref; stack[sp + 1] = __float_as_uint(v.rtc);
+            stack[sp] = v.ref[c]; stack[sp + 1] = __float_as_uint(v.tc[c]);
             sp += 2;
-            ref = v.lref; ref_tc = v.ltc;
-        } else if (v.hl) { ref = v.lref; ref_tc = v.ltc; }
-        else if (v.hr) { ref = v.rref; ref_tc = v.rtc; }
-        else {
+        }
+        if (!have) {
             if (sp == 0) break;
             sp -= 2;
             ref = stack[sp];

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
                 } else {
                     vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                     NodeVisit v = index_visit(S, S.iroot, inv, o * inv);
-                    enters = v.hl || v.hr;
+                    enters = v.hit[0] || v.hit[1] || v.hit[2] || v.hit[3];
                 }
             }
         }
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // idle lanes REFILL from the queue.  Every iteration the warp votes and executes the kind most
 // lanes are ready for, which keeps lanes busy although rays need between one and several
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
-constexpr int kStackWords = 64;  // per lane: inner-node stack from the bottom, noted leaves (2 words) from the top
+constexpr int kStackWords = 72;  // per lane: inner-node stack from the bottom, noted leaves (2 words) from the top
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kVisitQuorum = 20;  // at least this many lanes ready to visit: skip the full vote
 
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
 
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
-        bool room = sp + 2 * nl + 4 <= kStackWords;
+        bool room = sp + 2 * nl + 8 <= kStackWords;
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
         const bool canV = active && node != kNone && room;
         const unsigned mV = __ballot_sync(kFullMask, canV);
@@ -142,16 +142,23 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
             if (canV) {
                 if (STATS) ++visits;
                 NodeVisit v = index_visit(S, node, inv, oi);
-                const bool lleaf = (v.lref & IREF_LEAF) != 0, rleaf = (v.rref & IREF_LEAF) != 0;
-                const bool pl = v.hl && lleaf, pr = v.hr && rleaf;    // leaves to note
-                const bool il = v.hl && !lleaf, ir = v.hr && !rleaf;  // inner children to visit
                 const int spm = sp > 0 ? sp - 1 : 0;
                 const uint32_t top = stk[spm];
-                if (pl) { ++nl; stk[kStackWords - 2 * nl] = v.lref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.ltc); }
-                if (pr) { ++nl; stk[kStackWords - 2 * nl] = v.rref; stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.rtc); }
-                if (il && ir) { stk[sp] = v.rref; ++sp; }
-                const bool pop = !il && !ir && sp > 0;
-                node = il ? v.lref : (ir ? v.rref : (pop ? top : kNone));
+                uint32_t next = kNone;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool leaf = (v.ref[c] & IREF_LEAF) != 0;
+                    if (v.hit[c] && leaf) {  // note the leaf, test it later
+                        ++nl;
+                        stk[kStackWords - 2 * nl] = v.ref[c];
+                        stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.tc[c]);
+                    }
+                    const bool inner = v.hit[c] && !leaf;
+                    if (inner && next != kNone) { stk[sp] = v.ref[c]; ++sp; }
+                    next = (inner && next == kNone) ? v.ref[c] : next;
+                }
+                const bool pop = next == kNone && sp > 0;
+                node = pop ? top : next;
                 sp = pop ? spm : sp;
             }
         } else if (kind == kLeaf) {

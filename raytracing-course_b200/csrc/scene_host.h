@@ -60,7 +60,7 @@ struct FlatScene {
     std::vector<f4> xf_pos;            // (pos.xyz, bits(type|flags))
     std::vector<f4> xf_rot;            // quaternion xyzw
     std::vector<f4> mat0, mat1;        // (col.rgb, bits(material)) (emission.rgb, ior)
-    // index BVH (binary, both child boxes in the node): 4 x f4 per node
+    // index BVH (4-wide, all child boxes in the node): 8 x f4 = 128 bytes per node
     std::vector<f4> inodes;
     uint32_t iroot = 0;  // child reference of the root (may be a leaf reference)
     // reference BVH: 2 x f4 per node (centre.xyz, bits(left)) (half.xyz, bits(right)) + meta

@@ -71,7 +71,7 @@ def test_host_scene_matches_oracle(rtc, oracle_scenes, name):
     assert np.array_equal(sn[1], an[1])
     assert sn[2] == an[2]
     st = s.stats()
-    assert st["units"] >= 1 and st["index_nodes"] == st["units"] - 1
+    assert st["units"] >= 1 and st["index_nodes"] <= max(st["units"] - 1, 0)
     s.close()
 
 

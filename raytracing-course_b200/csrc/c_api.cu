@@ -65,17 +65,17 @@ struct rtc_scene {
     uint64_t batch_paths = kDefaultBatchPaths;
     uint64_t device_bytes = 0;
     // scene arrays in HBM
-    DevBuf<float4> geo0, geo1, geo2, xf_pos, xf_rot, mat0, mat1, inodes, rnodes;
-    DevBuf<uint4> rmeta;
-    DevBuf<uint32_t> lca;
-    DevBuf<int32_t> lights;
+    // one device arena + one pinned host mirror: a scene upload is a single H2D copy
+    unsigned char* arena_dev = nullptr;
+    unsigned char* arena_host = nullptr;  // cudaMallocHost
+    size_t arena_bytes = 0;
+    DevScene slices{};                    // pointers into arena_dev (scalars filled by dev())
     // wavefront state
     DevBuf<float4> path[2][4];
-    DevBuf<float> hit_cd;
-    DevBuf<uint32_t> hit_id;
+    DevBuf<float> hit_cd[2];             // ping-pong like the path queues
+    DevBuf<uint32_t> hit_id[2];
     DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
     DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
-    DevBuf<float4> planes;
     DevBuf<unsigned long long> stats;    // 8 words
     DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
     DevBuf<uint8_t> rgb;
@@ -121,9 +121,9 @@ struct rtc_scene {
     DevScene dev() const {
         DevScene S;
         std::memset(&S, 0, sizeof S);
-        S.geo0 = geo0.p; S.geo1 = geo1.p; S.geo2 = geo2.p; S.xf_pos = xf_pos.p; S.xf_rot = xf_rot.p;
-        S.mat0 = mat0.p; S.mat1 = mat1.p; S.inodes = inodes.p; S.rnodes = rnodes.p; S.rmeta = rmeta.p;
-        S.lca = lca.p; S.lights = lights.p; S.planes = planes.p;
+        S.geo0 = slices.geo0; S.geo1 = slices.geo1; S.geo2 = slices.geo2; S.xf_pos = slices.xf_pos; S.xf_rot = slices.xf_rot;
+        S.mat0 = slices.mat0; S.mat1 = slices.mat1; S.inodes = slices.inodes; S.rnodes = slices.rnodes; S.rmeta = slices.rmeta;
+        S.lca = slices.lca; S.lights = slices.lights; S.planes = slices.planes;
         S.nplanes = (uint32_t)(host.flat.planes.size() / 2);
         S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
         S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
@@ -142,10 +142,14 @@ struct rtc_scene {
         return S;
     }
     void release_device() {
-        geo0.release(); geo1.release(); geo2.release(); xf_pos.release(); xf_rot.release(); mat0.release(); mat1.release();
-        inodes.release(); rnodes.release(); rmeta.release(); lca.release(); lights.release(); planes.release();
+        if (arena_dev) cudaFree(arena_dev);
+        if (arena_host) cudaFreeHost(arena_host);
+        arena_dev = arena_host = nullptr;
+        arena_bytes = 0;
         for (auto& set : path) for (auto& b : set) b.release();
-        hit_cd.release(); hit_id.release(); trav_queue.release(); queue.release(); stats.release(); accum.release(); rgb.release();
+        for (auto& b : hit_cd) b.release();
+        for (auto& b : hit_id) b.release();
+        trav_queue.release(); queue.release(); stats.release(); accum.release(); rgb.release();
         collect_spans();
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
         event_pool.clear();
@@ -154,34 +158,49 @@ struct rtc_scene {
 
 namespace {
 
-template <class T, class H>
-int upload(DevBuf<T>& dst, const std::vector<H>& src, uint64_t& bytes) {
-    static_assert(sizeof(T) == sizeof(H), "layout mismatch");
-    CU(dst.ensure(src.size() ? src.size() : 1));
-    if (!src.empty()) CU(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(H), cudaMemcpyHostToDevice));
-    bytes += src.size() * sizeof(H);
-    return RTC_OK;
-}
-
+// Lays the flat scene arrays out in one arena (256-byte aligned slices).  First call: allocates
+// the device arena and its pinned host mirror and fills the mirror; every call: ONE async H2D copy.
 int upload_scene(rtc_scene* s, uint64_t* h2d) {
     if (s->device < 0) return fail(RTC_ERR_NO_DEVICE, "scene has no CUDA device");
     CU(cudaSetDevice(s->device));
     const FlatScene& F = s->host.flat;
-    uint64_t bytes = 0;
-    int rc;
-    if ((rc = upload(s->geo0, F.geo0, bytes))) return rc;
-    if ((rc = upload(s->geo1, F.geo1, bytes))) return rc;
-    if ((rc = upload(s->geo2, F.geo2, bytes))) return rc;
-    if ((rc = upload(s->xf_pos, F.xf_pos, bytes))) return rc;
-    if ((rc = upload(s->xf_rot, F.xf_rot, bytes))) return rc;
-    if ((rc = upload(s->mat0, F.mat0, bytes))) return rc;
-    if ((rc = upload(s->mat1, F.mat1, bytes))) return rc;
-    if ((rc = upload(s->inodes, F.inodes, bytes))) return rc;
-    if ((rc = upload(s->rnodes, F.rnodes, bytes))) return rc;
-    if ((rc = upload(s->rmeta, F.rmeta, bytes))) return rc;
-    if ((rc = upload(s->lca, F.lca, bytes))) return rc;
-    if ((rc = upload(s->lights, F.lights, bytes))) return rc;
-    if ((rc = upload(s->planes, F.planes, bytes))) return rc;
+    struct Part { const void* src; size_t bytes; size_t off; };
+    Part parts[] = {
+        {F.geo0.data(), F.geo0.size() * sizeof(f4), 0},     {F.geo1.data(), F.geo1.size() * sizeof(f4), 0},
+        {F.geo2.data(), F.geo2.size() * sizeof(f4), 0},     {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4), 0},
+        {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4), 0}, {F.mat0.data(), F.mat0.size() * sizeof(f4), 0},
+        {F.mat1.data(), F.mat1.size() * sizeof(f4), 0},     {F.inodes.data(), F.inodes.size() * sizeof(f4), 0},
+        {F.rnodes.data(), F.rnodes.size() * sizeof(f4), 0}, {F.rmeta.data(), F.rmeta.size() * sizeof(u4), 0},
+        {F.lca.data(), F.lca.size() * sizeof(uint32_t), 0}, {F.lights.data(), F.lights.size() * sizeof(int32_t), 0},
+        {F.planes.data(), F.planes.size() * sizeof(f4), 0},
+    };
+    size_t total = 0, payload = 0;
+    for (Part& p : parts) {
+        p.off = total;
+        total += (p.bytes + 255) & ~(size_t)255;
+        payload += p.bytes;
+    }
+    if (total == 0) total = 256;
+    if (!s->arena_dev) {
+        CU(cudaMalloc(&s->arena_dev, total));
+        CU(cudaMallocHost(&s->arena_host, total));
+        std::memset(s->arena_host, 0, total);
+        for (const Part& p : parts)
+            if (p.bytes) std::memcpy(s->arena_host + p.off, p.src, p.bytes);
+        s->arena_bytes = total;
+        unsigned char* base = s->arena_dev;
+        DevScene& D = s->slices;
+        D.geo0 = (const float4*)(base + parts[0].off);   D.geo1 = (const float4*)(base + parts[1].off);
+        D.geo2 = (const float4*)(base + parts[2].off);   D.xf_pos = (const float4*)(base + parts[3].off);
+        D.xf_rot = (const float4*)(base + parts[4].off); D.mat0 = (const float4*)(base + parts[5].off);
+        D.mat1 = (const float4*)(base + parts[6].off);   D.inodes = (const float4*)(base + parts[7].off);
+        D.rnodes = (const float4*)(base + parts[8].off); D.rmeta = (const uint4*)(base + parts[9].off);
+        D.lca = (const uint32_t*)(base + parts[10].off); D.lights = (const int32_t*)(base + parts[11].off);
+        D.planes = (const float4*)(base + parts[12].off);
+    }
+    CU(cudaMemcpyAsync(s->arena_dev, s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    const uint64_t bytes = payload;
     CU(s->queue.ensure(3 * kMaxDepthSlots));
     if (!s->stats.p) {
         CU(s->stats.ensure(8));
@@ -264,8 +283,8 @@ struct Staged {
 
 int ensure_wavefront(rtc_scene* s, uint64_t cap) {
     for (auto& set : s->path) for (auto& b : set) CU(b.ensure(cap));
-    CU(s->hit_cd.ensure(cap));
-    CU(s->hit_id.ensure(cap));
+    for (auto& b : s->hit_cd) CU(b.ensure(cap));
+    for (auto& b : s->hit_id) CU(b.ensure(cap));
     CU(s->trav_queue.ensure(cap));
     return RTC_OK;
 }
@@ -504,38 +523,30 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     cudaStream_t st = (cudaStream_t)stream;
     LaunchCtx c{st, s->sms};
     DevScene S = s->dev();
-    HitSoA H{s->hit_cd.p, s->hit_id.p};
-    uint32_t* tqc = s->queue.p + kMaxDepthSlots;      // rays queued for k_traverse, per bounce
+    uint32_t* tqc = s->queue.p + kMaxDepthSlots;        // rays queued for k_traverse, per bounce
     uint32_t* cursor = s->queue.p + 2 * kMaxDepthSlots; // k_traverse work cursors, per bounce
     for (uint64_t first = 0; first < total; first += cap) {
         uint32_t count = (uint32_t)((total - first) < cap ? (total - first) : cap);
         CU(cudaMemsetAsync(s->queue.p, 0, 3 * kMaxDepthSlots * sizeof(uint32_t), st));
         PathSoA cur{s->path[0][0].p, s->path[0][1].p, s->path[0][2].p, s->path[0][3].p};
         PathSoA nxt{s->path[1][0].p, s->path[1][1].p, s->path[1][2].p, s->path[1][3].p};
+        HitSoA hcur{s->hit_cd[0].p, s->hit_id[0].p}, hnxt{s->hit_cd[1].p, s->hit_id[1].p};
         s->span_begin(0, st);
-        launch_generate(c, S, cur, s->queue.p, first, count, seed, sample_begin);
+        launch_generate(c, S, cur, hcur, s->queue.p, s->trav_queue.p, tqc, first, count, seed, sample_begin);
         s->span_end(st);
         s->launches++;
         for (uint32_t b = 1; b <= depth; ++b) {
-            if (s->traversal == RTC_TRAVERSAL_REFTREE) {
-                s->span_begin(1, st);
-                launch_extend_reftree(c, S, cur, H, s->queue.p + (b - 1), count);
-                s->span_end(st);
-                s->launches += 1;
-            } else {
-                s->span_begin(3, st);
-                launch_pre(c, S, cur, H, s->queue.p + (b - 1), count, s->trav_queue.p, tqc + (b - 1));
-                s->span_end(st);
-                s->span_begin(1, st);
-                launch_traverse(c, S, cur, H, count, s->trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
-                s->span_end(st);
-                s->launches += 2;
-            }
-            s->span_begin(2, st);
-            launch_shade(c, S, cur, H, nxt, s->queue.p + (b - 1), s->queue.p + b, count, accum_dev, b, seed);
+            s->span_begin(1, st);
+            if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, s->queue.p + (b - 1), count);
+            else launch_traverse(c, S, cur, hcur, count, s->trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
             s->span_end(st);
-            s->launches += 1;
+            s->span_begin(2, st);
+            launch_shade(c, S, cur, hcur, nxt, hnxt, s->queue.p + (b - 1), s->queue.p + b, s->trav_queue.p, tqc + b, count,
+                         accum_dev, b, seed);
+            s->span_end(st);
+            s->launches += 2;
             PathSoA tmp = cur; cur = nxt; nxt = tmp;
+            HitSoA htmp = hcur; hcur = hnxt; hnxt = htmp;
         }
         launch_tally(c, s->queue.p, tqc, depth, s->stats.p);
         s->launches++;

@@ -18,33 +18,70 @@ namespace rtc {
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = 32;           // queue slots a warp reserves per atomic
 
+// Planes (src/scene.cpp:50-66) and the root of the index BVH for one fresh ray: cd = closest_dist
+// handed to BVH_t::Intersect, id = the plane hit so far; returns whether the ray touches any
+// child box of the index root (only those rays are queued for k_traverse).
+RT_D bool pre_step(const DevScene& S, vec3 o, vec3 d, float& cd, uint32_t& id) {
+    int pid;
+    closest_plane(S, o, d, cd, pid);
+    id = pid < 0 ? HIT_MISS : (uint32_t)pid;
+    if (S.iroot == IREF_NONE) return false;
+    if (S.iroot & IREF_LEAF) {
+        float te; bool interior; uint32_t l, r;
+        return ref_box(S, S.root, o, d, te, interior, l, r);
+    }
+    vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    NodeVisit v = index_visit(S, S.iroot, inv, o * inv);
+    return v.hit[0] || v.hit[1] || v.hit[2] || v.hit[3];
+}
+// warp-aggregated append of slot `i` to the traverse queue; call with the full warp converged
+RT_D void enqueue(bool enters, uint32_t i, uint32_t* tq, uint32_t* tq_count, uint32_t lane) {
+    unsigned mask = __ballot_sync(kFullMask, enters);
+    if (mask) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(tq_count, (uint32_t)__popc(mask));
+        base = __shfl_sync(kFullMask, base, 0);
+        if (enters) tq[base + __popc(mask & ((1u << lane) - 1u))] = i;
+    }
+}
+
 // ------------------------------------------------------------------------------- generate
 // Scene::Sample's jitter + Camera::GetToRay (src/scene.cpp:189-200): one thread per path.
 // Path ids run sample-major over the image: consecutive threads = consecutive pixels of a row.
-__global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, uint32_t* q, uint64_t first_path, uint32_t count,
-                                                   uint32_t seed, uint32_t sample_begin) {
+__global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, HitSoA H, uint32_t* q, uint32_t* tq, uint32_t* tq_count,
+                                                   uint64_t first_path, uint32_t count, uint32_t seed, uint32_t sample_begin) {
     const uint32_t npix = S.width * S.height;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        uint64_t pid = first_path + i;
-        uint32_t sample = sample_begin + (uint32_t)(pid / npix);
-        uint32_t pixel = (uint32_t)(pid % npix);
-        uint32_t x = pixel % S.width, y = pixel / S.width;
-        Rng g{seed, pixel, sample, 0};
-        uint4 b = g.block(0);
-        float fx = __fadd_rn((float)x, u01(b.x)), fy = __fadd_rn((float)y, u01(b.y));
-        vec3 o, d;
-        camera_ray(S, fx, fy, o, d);
-        P.o[i] = make_float4(o.x, o.y, o.z, 0.f);
-        P.d[i] = make_float4(d.x, d.y, d.z, 0.f);
-        P.beta[i] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
-        P.rad[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample));
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rounded = (count + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool enters = false;
+        if (i < count) {
+            uint64_t pid = first_path + i;
+            uint32_t sample = sample_begin + (uint32_t)(pid / npix);
+            uint32_t pixel = (uint32_t)(pid % npix);
+            uint32_t x = pixel % S.width, y = pixel / S.width;
+            Rng g{seed, pixel, sample, 0};
+            uint4 b = g.block(0);
+            float fx = __fadd_rn((float)x, u01(b.x)), fy = __fadd_rn((float)y, u01(b.y));
+            vec3 o, d;
+            camera_ray(S, fx, fy, o, d);
+            P.o[i] = make_float4(o.x, o.y, o.z, 0.f);
+            P.d[i] = make_float4(d.x, d.y, d.z, 0.f);
+            P.beta[i] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
+            P.rad[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample));
+            float cd; uint32_t id;
+            enters = pre_step(S, o, d, cd, id);
+            H.cd[i] = cd;
+            H.id[i] = id;
+        }
+        enqueue(enters, i, tq, tq_count, lane);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) q[0] = count;
 }
 
 // ------------------------------------------------------------------------------- extend, step 1
-// Planes (src/scene.cpp:50-66) and the root of the index BVH.  H.cd = closest_dist handed to
-// BVH_t::Intersect, H.id = the plane hit so far.
+// pre_step as a kernel of its own: only the probe path (rtc_intersect) needs it -- in a render the
+// step is fused into the kernel that creates the ray (k_generate, k_shade).
 __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t* tq,
                                               uint32_t* tq_count) {
     const uint32_t count = *qcount;
@@ -53,30 +90,12 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool enters = false;
         if (i < count) {
-            vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
-            float closest;
-            int id;
-            closest_plane(S, o, d, closest, id);
-            H.cd[i] = closest;
-            H.id[i] = id < 0 ? HIT_MISS : (uint32_t)id;
-            if (S.iroot != IREF_NONE) {
-                if (S.iroot & IREF_LEAF) {
-                    float te; bool interior; uint32_t l, r;
-                    enters = ref_box(S, S.root, o, d, te, interior, l, r);
-                } else {
-                    vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                    NodeVisit v = index_visit(S, S.iroot, inv, o * inv);
-                    enters = v.hit[0] || v.hit[1] || v.hit[2] || v.hit[3];
-                }
-            }
+            float cd; uint32_t id;
+            enters = pre_step(S, ld3(P.o[i]), ld3(P.d[i]), cd, id);
+            H.cd[i] = cd;
+            H.id[i] = id;
         }
-        unsigned mask = __ballot_sync(kFullMask, enters);
-        if (mask) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(tq_count, (uint32_t)__popc(mask));
-            base = __shfl_sync(kFullMask, base, 0);
-            if (enters) tq[base + __popc(mask & ((1u << lane) - 1u))] = i;
-        }
+        enqueue(enters, i, tq, tq_count, lane);
     }
 }
 
@@ -249,8 +268,9 @@ RT_D void deposit(float* accum, uint32_t pixel, vec3 L) {
 // Scene::RayTrace's material switch (src/scene.cpp:96-177) for one bounce, recursion unrolled:
 // L = sum_k beta_k * E_k.  Surviving paths are written compacted (warp ballot + one atomic per
 // warp) into the next queue; finished paths add their radiance to the pixel sum.
-__global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, const uint32_t* qin, uint32_t* qout,
-                                                float* accum, uint32_t bounce, uint32_t seed) {
+__global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
+                                                uint32_t* qout, uint32_t* tq, uint32_t* tq_count, float* accum, uint32_t bounce,
+                                                uint32_t seed) {
     const uint32_t count = *qin;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t rounded = (count + 31u) & ~31u;
@@ -327,17 +347,25 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, 
             if (!alive) deposit(accum, pixel, L);
         }
         unsigned mask = __ballot_sync(kFullMask, alive);
+        bool enters = false;
+        uint32_t dst = 0;
         if (mask) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(qout, (uint32_t)__popc(mask));
             base = __shfl_sync(kFullMask, base, 0);
             if (alive) {
-                uint32_t dst = base + __popc(mask & ((1u << lane) - 1u));
+                dst = base + __popc(mask & ((1u << lane) - 1u));
                 N.o[dst] = make_float4(no.x, no.y, no.z, 0.f);
                 N.d[dst] = make_float4(nd.x, nd.y, nd.z, 0.f);
                 N.beta[dst] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(pixel));
                 N.rad[dst] = make_float4(L.x, L.y, L.z, __uint_as_float(sample));
+                // first part of the next Scene::RayIntersection, while the ray is still in registers
+                float cd; uint32_t id;
+                enters = pre_step(S, no, nd, cd, id);
+                HN.cd[dst] = cd;
+                HN.id[dst] = id;
             }
+            enqueue(enters, dst, tq, tq_count, lane);
         }
     }
 }
@@ -440,9 +468,9 @@ static int grid_for(uint64_t n, int block, int sms, int per_sm) {
     return (int)(want < cap ? want : cap);
 }
 
-void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, uint32_t* q, uint64_t first_path, uint32_t count,
-                     uint32_t seed, uint32_t sample_begin) {
-    k_generate<<<grid_for(count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, q, first_path, count, seed, sample_begin);
+void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t* q, uint32_t* tq, uint32_t* tq_count,
+                     uint64_t first_path, uint32_t count, uint32_t seed, uint32_t sample_begin) {
+    k_generate<<<grid_for(count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, H, q, tq, tq_count, first_path, count, seed, sample_begin);
 }
 void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
                 uint32_t* tq, uint32_t* tq_count) {
@@ -466,9 +494,10 @@ void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H,
 void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count) {
     k_extend_reftree<<<grid_for(max_count, 128, c.sms, 16), 128, 0, c.stream>>>(S, P, H, qcount);
 }
-void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, const uint32_t* qin, uint32_t* qout,
-                  uint32_t max_count, float* accum, uint32_t bounce, uint32_t seed) {
-    k_shade<<<grid_for(max_count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, H, N, qin, qout, accum, bounce, seed);
+void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
+                  uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float* accum, uint32_t bounce,
+                  uint32_t seed) {
+    k_shade<<<grid_for(max_count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
 }
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     k_tally<<<1, 1, 0, c.stream>>>(q, tqc, ray_depth, stats);

@@ -12,8 +12,9 @@ struct LaunchCtx {
     int sms;  // multiprocessor count of the device (grid sizing)
 };
 
-void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, uint32_t* q, uint64_t first_path, uint32_t count,
-                     uint32_t seed, uint32_t sample_begin);
+// camera rays of one wavefront batch + their pre_step (planes, index root, traverse queue)
+void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t* q, uint32_t* tq, uint32_t* tq_count,
+                     uint64_t first_path, uint32_t count, uint32_t seed, uint32_t sample_begin);
 // Scene::RayIntersection for the rays of queue P (fills H): launch_pre then launch_traverse
 // (index BVH), or launch_extend_reftree alone (the reference-tree twin).
 void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
@@ -21,8 +22,10 @@ void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, cons
 void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t max_count, const uint32_t* tq,
                      const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats);
 void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count);
-void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, const uint32_t* qin, uint32_t* qout,
-                  uint32_t max_count, float* accum, uint32_t bounce, uint32_t seed);
+// shading of queue P with hits H; survivors go to queue N with their pre_step results in HN / tq
+void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
+                  uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float* accum, uint32_t bounce,
+                  uint32_t seed);
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats);
 void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out);
 void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out);

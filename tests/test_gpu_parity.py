@@ -151,7 +151,8 @@ def squash(x):
 
 
 @pytest.mark.parametrize("name,w,h,spp", [("practice5_1", 64, 48, 4), ("practice5_2", 64, 48, 8), ("lights_mix", 96, 64, 8),
-                                          ("practice5_dragon_10k", 64, 64, 4)])
+                                          ("practice5_dragon_10k", 64, 64, 4), ("practice5_dragon_100k_glass", 40, 40, 2),
+                                          ("practice5_dragon_100k_metal", 40, 40, 2), ("practice5_dragon_100k_glow", 40, 40, 2)])
 def test_render_sample_exact_vs_oracle(rtc, oracle_lib, name, w, h, spp):
     """Same Philox streams on both sides: per-pixel radiance sums agree to float rounding except
     where a path crosses a discontinuity differently (a handful of pixels)."""

@@ -48,12 +48,13 @@ struct Rng {
 RT_D float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 RT_D void box_muller(uint32_t x0, uint32_t x1, float& z0, float& z1) {
     float a = (float)((x0 >> 8) + 1u) * (1.0f / 16777216.0f);
-    float r = sqrtf(-2.0f * logf(a));
-    float th = 6.283185307179586f * u01(x1);
+    float r = sqrtf(-2.0f * __logf(a));
+    // theta in [0, 2pi): evaluate at theta - pi in [-pi, pi), where the fast sin/cos are accurate
+    float th = 6.283185307179586f * u01(x1) - 3.14159265358979f;
     float s, c;
-    sincosf(th, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    __sincosf(th, &s, &c);
+    z0 = -r * c;
+    z1 = -r * s;
 }
 // Distribution::SampleNormal01Vec, src/distributions.cpp:102-110
 RT_D vec3 normal_vec(uint4 b) {
@@ -64,6 +65,17 @@ RT_D vec3 normal_vec(uint4 b) {
 }
 
 // ------------------------------------------------------------------------------- primitives
+// Two arithmetic flavours.  EXACT (default) keeps IEEE division / sqrt wherever a result decides a
+// hit or becomes the reported distance or normal (traversal, final hit, rtc_intersect).  FAST
+// (approximate reciprocal / rsqrt, <= 2 ulp) is used only inside the shading estimators
+// (light pdf, validity test of a light sample), whose inputs are random anyway.
+template <bool FAST> RT_D float rt_div(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+template <bool FAST> RT_D vec3 rt_div(vec3 a, vec3 b) { return mk3(rt_div<FAST>(a.x, b.x), rt_div<FAST>(a.y, b.y), rt_div<FAST>(a.z, b.z)); }
+template <bool FAST> RT_D vec3 rt_normalize(vec3 a) {
+    if (!FAST) return normalize(a);
+    float k = rsqrtf(dot(a, a));
+    return mk3(a.x * k, a.y * k, a.z * k);
+}
 struct Isect {
     float t;
     vec3 n;
@@ -84,22 +96,31 @@ RT_D bool isect_plane(vec3 o, vec3 d, vec3 n, Isect& out) {
     return false;
 }
 // Primitive::IntersectBox, src/primitives.cpp:70-117
+template <bool FAST = false>
 RT_D bool isect_box(vec3 o, vec3 d, vec3 s, Isect& out) {
-    vec3 a = (-s - o) / d, b = (s - o) / d;
+    vec3 a, b;
+    if (FAST) {
+        vec3 inv = mk3(__fdividef(1.f, d.x), __fdividef(1.f, d.y), __fdividef(1.f, d.z));
+        a = (-s - o) * inv;
+        b = (s - o) * inv;
+    } else {
+        a = (-s - o) / d;
+        b = (s - o) / d;
+    }
     float t1 = fmaxf(fmaxf(fminf(a.x, b.x), fminf(a.y, b.y)), fminf(a.z, b.z));
     float t2 = fminf(fminf(fmaxf(a.x, b.x), fmaxf(a.y, b.y)), fmaxf(a.z, b.z));
     if (t1 > t2 || t2 < 0.f) return false;
     bool interior = t1 < 0.f;
     float t = interior ? t2 : t1;
     vec3 p = o + t * d;
-    vec3 nrm = p / s;
+    vec3 nrm = rt_div<FAST>(p, s);
     if (interior) nrm = -nrm;
     float mx = fmaxf(fmaxf(fabsf(nrm.x), fabsf(nrm.y)), fabsf(nrm.z));
     if (fabsf(nrm.x) != mx) nrm.x = 0.f;
     if (fabsf(nrm.y) != mx) nrm.y = 0.f;
     if (fabsf(nrm.z) != mx) nrm.z = 0.f;
     out.t = t;
-    out.n = normalize(nrm);
+    out.n = rt_normalize<FAST>(nrm);
     out.interior = interior;
     return true;
 }
@@ -159,6 +180,7 @@ RT_D void to_local(const DevScene& S, uint32_t prim, uint32_t flags, vec3& o, ve
 RT_D uint32_t prim_flags(const DevScene& S, uint32_t prim) { return __float_as_uint(__ldg(&S.xf_pos[prim].w)); }
 
 // distance-only test used during traversal (normal is recomputed once for the winner)
+template <bool FAST = false>
 RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t) {
     uint32_t flags = prim_flags(S, prim);
     to_local(S, prim, flags, o, d);
@@ -171,7 +193,7 @@ RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t)
     Isect is;
     bool ok;
     switch (flags & PF_TYPE_MASK) {
-        case PT_BOX: ok = isect_box(o, d, ld3(g0), is); break;
+        case PT_BOX: ok = isect_box<FAST>(o, d, ld3(g0), is); break;
         case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), is); break;
         default: ok = isect_plane(o, d, ld3(g0), is); break;
     }
@@ -179,6 +201,7 @@ RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t)
     return ok;
 }
 // Primitive::Intersect, src/primitives.cpp:14-52 (normal back to world space, re-normalised)
+template <bool FAST = false>
 RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect& out) {
     uint32_t flags = prim_flags(S, prim);
     to_local(S, prim, flags, o, d);
@@ -194,7 +217,7 @@ RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect
             out.n = interior ? -n : n;
             break;
         }
-        case PT_BOX: ok = isect_box(o, d, ld3(g0), out); break;
+        case PT_BOX: ok = isect_box<FAST>(o, d, ld3(g0), out); break;
         case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), out); break;
         default: ok = isect_plane(o, d, ld3(g0), out); break;
     }
@@ -205,7 +228,7 @@ RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect
         q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
         out.n = rotate(q, out.n);
     }
-    out.n = normalize(out.n);
+    out.n = rt_normalize<FAST>(out.n);
     return true;
 }
 
@@ -530,7 +553,7 @@ RT_D vec3 sample_box(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
         vec3 on_box = rotate(q, pnt) + pos;
         smp = normalize(on_box - x);
         float t;
-        if (prim_hit_t(S, prim, x, smp, t)) break;
+        if (prim_hit_t<true>(S, prim, x, smp, t)) break;
     }
     return smp;
 }
@@ -546,7 +569,7 @@ RT_D vec3 sample_ellipsoid(const DevScene& S, uint32_t prim, const Rng& g, vec3 
         vec3 on = rotate(q, r * k) + pos;
         smp = normalize(on - x);
         float t;
-        if (prim_hit_t(S, prim, x, smp, t)) break;
+        if (prim_hit_t<true>(S, prim, x, smp, t)) break;
     }
     return smp;
 }
@@ -574,20 +597,20 @@ RT_D float pdf_point(const DevScene& S, uint32_t prim, bool is_box, float dist2,
         vec3 n = rotate(qc, y - pos) / r;
         p_y = 1.f / (4.f * kPi * length(mk3(n.x * r.y * r.z, r.x * n.y * r.z, r.x * r.y * n.z)));
     }
-    return p_y * dist2 / fabsf(dot(d, nrm));
+    return __fdividef(p_y * dist2, fabsf(dot(d, nrm)));
 }
 // PdfBox / PdfEllipsoid + GetPointsForPdf, src/distributions.cpp:170-198, 289-312, 349-372
 RT_D float pdf_light(const DevScene& S, uint32_t prim, vec3 x, vec3 d) {
     bool is_box = (prim_flags(S, prim) & PF_TYPE_MASK) == PT_BOX;
     Isect i1;
-    if (!prim_intersect(S, prim, x, d, i1)) return 1e-9f;
+    if (!prim_intersect<true>(S, prim, x, d, i1)) return 1e-9f;
     if (i1.t <= 1e-8f) return 1e-9f;
     vec3 p1 = x + i1.t * d;
     vec3 v1 = p1 - x;
     float sum = pdf_point(S, prim, is_box, dot(v1, v1), p1, i1.n, d);
     float step = i1.t + 1e-4f;
     Isect i2;
-    if (prim_intersect(S, prim, x + step * d, d, i2)) {
+    if (prim_intersect<true>(S, prim, x + step * d, d, i2)) {
         float t2 = i2.t + step;
         vec3 p2 = x + t2 * d;
         vec3 v2 = p2 - x;

@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, 
                         float cs = dot(dir, normal);
                         if (cs > 0.f) {
                             float pw = mix_pdf(S, p_outer, normal, dir);
-                            vec3 w = mk3(col.x / kPi, col.y / kPi, col.z / kPi);
-                            float k2 = 1.f / pw;
+                            const float inv_pi = 1.f / kPi;
+                            vec3 w = mk3(col.x * inv_pi, col.y * inv_pi, col.z * inv_pi);
+                            float k2 = __fdividef(1.f, pw);
                             beta = beta * mk3(w.x * cs * k2, w.y * cs * k2, w.z * cs * k2);
                             no = p + kSceneEps * dir; nd = dir;
                             alive = true;

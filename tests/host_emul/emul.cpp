@@ -23,6 +23,10 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
+#define __logf logf        /* glibc declares __logf / __sincosf itself: map the CUDA fast intrinsics by macro */
+#define __sincosf sincosf
 
 #include "rt_device.cuh"
 

@@ -386,10 +386,24 @@ RT_D void slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
     hit = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
     tc = t1 < 0.f ? -kInfF : t1;
 }
+// 32-byte read-only load (LDG.E.256 on sm_100a)
+RT_D void ldg8(const float4* p, float4& a, float4& b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+#else
+    a = p[0];
+    b = p[1];
+#endif
+}
 RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) {
     const float4* nd = S.inodes + 8 * (size_t)node;
-    float4 ax = ldg4(nd), ay = ldg4(nd + 1), az = ldg4(nd + 2), bx = ldg4(nd + 3), by = ldg4(nd + 4), bz = ldg4(nd + 5);
-    float4 rf = ldg4(nd + 6);
+    float4 ax, ay, az, bx, by, bz, rf, pad;
+    ldg8(nd, ax, ay);
+    ldg8(nd + 2, az, bx);
+    ldg8(nd + 4, by, bz);
+    ldg8(nd + 6, rf, pad);
     NodeVisit v;
     v.ref[0] = __float_as_uint(rf.x); v.ref[1] = __float_as_uint(rf.y);
     v.ref[2] = __float_as_uint(rf.z); v.ref[3] = __float_as_uint(rf.w);

@@ -15,6 +15,7 @@
 // recursion is then replayed on just those leaves, using lowest-common-ancestor queries on
 // the reference tree (DESIGN.md "Traversal").
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -129,15 +130,57 @@ struct Unit {
     Aabb box;
     uint32_t first, count;
     vec3 centre;
+    bool fast;  // a single untransformed triangle: its box is min/max of its vertices
 };
+// float -> IEEE half bits, round to nearest even (finite inputs; overflow gives infinity)
+static uint16_t half_bits_rn(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x47800000u) return (uint16_t)(sign | 0x7C00u);           // >= 65536 (or inf/nan) -> inf
+    if (x < 0x38800000u) {                                             // subnormal half (or zero)
+        if (x < 0x33000000u) return (uint16_t)sign;
+        const uint32_t shift = 113u - (x >> 23);
+        const uint32_t mant = (x & 0x7FFFFFu) | 0x800000u;
+        uint32_t h = mant >> (shift + 13);
+        const uint32_t rem = mant & ((1u << (shift + 13)) - 1u), half = 1u << (shift + 12);
+        if (rem > half || (rem == half && (h & 1u))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((x - 0x38000000u) >> 13);
+    const uint32_t rem = x & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+}
+static float half_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+    float f;
+    if (e == 0) f = std::ldexp((float)m, -24);
+    else if (e == 31) f = m ? NAN : INFINITY;
+    else f = std::ldexp((float)(m | 0x400u), (int)e - 25);
+    return sign ? -f : f;
+}
+// the largest half <= f (down) / the smallest half >= f (up): conservative child boxes
+static uint16_t half_down(float f) {
+    uint16_t h = half_bits_rn(f);
+    if (half_to_float(h) > f) h = (h & 0x8000u) ? (uint16_t)(h + 1) : (h == 0 ? (uint16_t)0x8001u : (uint16_t)(h - 1));
+    return h;
+}
+static uint16_t half_up(float f) {
+    uint16_t h = half_bits_rn(f);
+    if (half_to_float(h) < f) h = (h & 0x8000u) ? (h == 0x8000u ? (uint16_t)0x0001u : (uint16_t)(h - 1)) : (uint16_t)(h + 1);
+    return h;
+}
+
 struct IndexBuilder {
     const std::vector<Unit>& units;
     std::vector<uint32_t> order;
-    std::vector<f4>& out;  // 8 f4 per 4-wide node
+    std::vector<f4>& out;  // 4 f4 (64 bytes) per 4-wide node
     std::vector<float> rarea;
     uint32_t max_depth = 0;
 
-    static uint32_t leaf_ref(const Unit& u) { return IREF_LEAF | ((u.count - 1) << 24) | u.first; }
+    static uint32_t leaf_ref(const Unit& u) { return IREF_LEAF | (u.fast ? IREF_FAST : 0u) | ((u.count - 1) << 24) | u.first; }
     static f4 bits4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
         f4 r;
         std::memcpy(&r.x, &a, 4); std::memcpy(&r.y, &b, 4); std::memcpy(&r.z, &c, 4); std::memcpy(&r.w, &d, 4);
@@ -212,21 +255,26 @@ struct IndexBuilder {
             slots[pick] = Slot{c.box[0], c.ref[0]};
             slots.push_back(Slot{c.box[1], c.ref[1]});
         }
-        uint32_t me = (uint32_t)(out.size() / 8);
-        out.resize(out.size() + 8, f4{0, 0, 0, 0});
-        float v[6][4];
+        uint32_t me = (uint32_t)(out.size() / 4);
+        out.resize(out.size() + 4, f4{0, 0, 0, 0});
+        uint16_t hv[6][4];
         uint32_t refs[4];
         for (int i = 0; i < 4; ++i) {
             bool used = i < (int)slots.size();
             // unused slot: a far-away point box and the IREF_NONE marker
-            Aabb bx = used ? slots[i].box : Aabb{{1e30f, 1e30f, 1e30f}, {1e30f, 1e30f, 1e30f}};
-            v[0][i] = bx.mn.x; v[1][i] = bx.mn.y; v[2][i] = bx.mn.z;
-            v[3][i] = bx.mx.x; v[4][i] = bx.mx.y; v[5][i] = bx.mx.z;
+            Aabb bx = used ? slots[i].box : Aabb{{60000.f, 60000.f, 60000.f}, {60000.f, 60000.f, 60000.f}};
+            hv[0][i] = half_down(bx.mn.x); hv[1][i] = half_down(bx.mn.y); hv[2][i] = half_down(bx.mn.z);
+            hv[3][i] = half_up(bx.mx.x); hv[4][i] = half_up(bx.mx.y); hv[5][i] = half_up(bx.mx.z);
             refs[i] = IREF_NONE;
             if (used) refs[i] = (slots[i].ref & IREF_LEAF) ? slots[i].ref : emit(slots[i].ref, depth + 1);
         }
-        for (int r = 0; r < 6; ++r) out[8 * me + r] = f4{v[r][0], v[r][1], v[r][2], v[r][3]};
-        out[8 * me + 6] = bits4(refs[0], refs[1], refs[2], refs[3]);
+        uint32_t w[16];
+        for (int r = 0; r < 6; ++r) {
+            w[2 * r] = (uint32_t)hv[r][0] | ((uint32_t)hv[r][1] << 16);
+            w[2 * r + 1] = (uint32_t)hv[r][2] | ((uint32_t)hv[r][3] << 16);
+        }
+        for (int i = 0; i < 4; ++i) w[12 + i] = refs[i];
+        for (int q = 0; q < 4; ++q) out[4 * me + q] = bits4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         return me;
     }
 };
@@ -325,8 +373,14 @@ void HostScene::init() {
             F.ref_depth = std::max(F.ref_depth, depth[v]);
             if (nd.left == UINT32_MAX) {
                 F.rmeta[v] = u4{nd.first, nd.count, depth[v], 0};
-                if (nd.count > IREF_MAX_LEAF_PRIMS) throw std::runtime_error("a BVH leaf holds more than 128 primitives");
-                if (nd.count > 0) units.push_back(Unit{nd.box, nd.first, nd.count, 0.5f * (nd.box.mx + nd.box.mn)});
+                if (nd.count > IREF_MAX_LEAF_PRIMS) throw std::runtime_error("a BVH leaf holds more than 64 primitives");
+                if (nd.count > 0) {
+                    const Primitive& p0 = prims[nd.first];
+                    bool ident = p0.rot.x == 0.f && p0.rot.y == 0.f && p0.rot.z == 0.f && p0.rot.w == 1.f &&
+                                 p0.pos.x == 0.f && p0.pos.y == 0.f && p0.pos.z == 0.f;
+                    bool fast = nd.count == 1 && p0.type == PT_TRIANGLE && ident;
+                    units.push_back(Unit{nd.box, nd.first, nd.count, 0.5f * (nd.box.mx + nd.box.mn), fast});
+                }
             } else {
                 F.rmeta[v] = u4{nd.first, nodes[nd.right].first, depth[v], 0};
                 depth[nd.left] = depth[nd.right] = depth[v] + 1;
@@ -337,6 +391,11 @@ void HostScene::init() {
     }
     std::sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.first < b.first; });
     F.units = (uint32_t)units.size();
+    F.ubox.assign(2 * (size_t)n, f4{0, 0, 0, 0});
+    for (const Unit& u : units) {
+        F.ubox[2 * (size_t)u.first] = f4{u.box.mn.x, u.box.mn.y, u.box.mn.z, 0.f};
+        F.ubox[2 * (size_t)u.first + 1] = f4{u.box.mx.x, u.box.mx.y, u.box.mx.z, 0.f};
+    }
 
     // ---- index BVH
     F.inodes.clear();

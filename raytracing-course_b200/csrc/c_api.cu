@@ -123,7 +123,7 @@ struct rtc_scene {
         std::memset(&S, 0, sizeof S);
         S.geo0 = slices.geo0; S.geo1 = slices.geo1; S.geo2 = slices.geo2; S.xf_pos = slices.xf_pos; S.xf_rot = slices.xf_rot;
         S.mat0 = slices.mat0; S.mat1 = slices.mat1; S.inodes = slices.inodes; S.rnodes = slices.rnodes; S.rmeta = slices.rmeta;
-        S.lca = slices.lca; S.lights = slices.lights; S.planes = slices.planes;
+        S.lca = slices.lca; S.lights = slices.lights; S.planes = slices.planes; S.ubox = slices.ubox;
         S.nplanes = (uint32_t)(host.flat.planes.size() / 2);
         S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
         S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
@@ -172,7 +172,7 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
         {F.mat1.data(), F.mat1.size() * sizeof(f4), 0},     {F.inodes.data(), F.inodes.size() * sizeof(f4), 0},
         {F.rnodes.data(), F.rnodes.size() * sizeof(f4), 0}, {F.rmeta.data(), F.rmeta.size() * sizeof(u4), 0},
         {F.lca.data(), F.lca.size() * sizeof(uint32_t), 0}, {F.lights.data(), F.lights.size() * sizeof(int32_t), 0},
-        {F.planes.data(), F.planes.size() * sizeof(f4), 0},
+        {F.planes.data(), F.planes.size() * sizeof(f4), 0}, {F.ubox.data(), F.ubox.size() * sizeof(f4), 0},
     };
     size_t total = 0, payload = 0;
     for (Part& p : parts) {
@@ -197,6 +197,7 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
         D.rnodes = (const float4*)(base + parts[8].off); D.rmeta = (const uint4*)(base + parts[9].off);
         D.lca = (const uint32_t*)(base + parts[10].off); D.lights = (const int32_t*)(base + parts[11].off);
         D.planes = (const float4*)(base + parts[12].off);
+        D.ubox = (const float4*)(base + parts[13].off);
     }
     CU(cudaMemcpyAsync(s->arena_dev, s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, nullptr));
     CU(cudaStreamSynchronize(nullptr));
@@ -333,7 +334,7 @@ int rtc_scene_info(const rtc_scene* s, uint32_t out[8]) {
 int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]) {
     if (!s || !out) return fail(RTC_ERR_ARG, "null argument");
     const FlatScene& F = s->host.flat;
-    out[0] = F.inodes.size() / 8; out[1] = F.index_depth; out[2] = F.ref_depth; out[3] = F.units;
+    out[0] = F.inodes.size() / 4; out[1] = F.index_depth; out[2] = F.ref_depth; out[3] = F.units;
     out[4] = s->device_bytes; out[5] = F.lca_levels; out[6] = 0; out[7] = 0;
     return RTC_OK;
 }

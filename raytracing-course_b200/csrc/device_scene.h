@@ -15,13 +15,14 @@ struct DevScene {
     const float4* xf_rot;  // quaternion xyzw
     const float4* mat0;    // (colour, bits(material))
     const float4* mat1;    // (emission, ior)
-    // index BVH: 8 float4 (128 B) per 4-wide node
+    // index BVH: 4 float4 (64 B) per 4-wide node, fp16 child boxes
     const float4* inodes;
     // reference BVH: 2 float4 per node + meta
     const float4* rnodes;
     const uint4* rmeta;
     const uint32_t* lca;
     const int32_t* lights;
+    const float4* ubox;    // per primitive slot: exact (min) (max) of the reference leaf that starts there
     const float4* planes;  // per plane: (n.xyz, bits(prim id)) (pos.xyz, bits(1 = no rotation))
 
     uint32_t nprims, nbvh, nnodes, root, iroot, lca_levels, nlights, ref_depth;

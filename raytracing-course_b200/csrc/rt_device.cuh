@@ -2,6 +2,7 @@
 // the two BVH traversals, the light/cosine mix distribution and the Philox streams.
 // Reference lines are cited per function (paths under /root/reference/hw5).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -368,13 +369,15 @@ RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, Leaf
     return cur;
 }
 
-// One index-BVH node = 4 child boxes in one 128-byte line (8 float4): min.x[4] min.y[4] min.z[4]
-// max.x[4] max.y[4] max.z[4] refs[4] pad.  Slab tests in min/max form with the reciprocal
-// direction; the same expression is used at every level, so a hit child box implies hit ancestor
-// boxes.  tc = box entry distance, or -inf when the origin is inside (the reference's `interior`).
+// One index-BVH node = 64 bytes: the boxes of its 4 children as fp16 rounded OUTWARD
+// (min.x[4] min.y[4] min.z[4] max.x[4] | max.y[4] max.z[4] refs[4]), read with two 32-byte loads.
+// The traversal is bound by the L1 misses an SM can keep in flight (profiles/r01_experiments.md),
+// so node bytes are what counts; conservative boxes only add candidates, and every leaf is
+// re-tested against its EXACT float box before its primitives are (leaf_test).
+// Slab tests in min/max form with the reciprocal direction.  tc = box entry distance, or -inf when
+// the origin is inside (the reference's `interior`).
 struct NodeVisit {
     uint32_t ref[4];
-    float tc[4];
     bool hit[4];
 };
 RT_D void slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 inv, vec3 oi, uint32_t ref, bool& hit, float& tc) {
@@ -397,25 +400,32 @@ RT_D void ldg8(const float4* p, float4& a, float4& b) {
     b = p[1];
 #endif
 }
+RT_D float2 unpack_half2(float word) {
+    uint32_t u = __float_as_uint(word);
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
 RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) {
-    const float4* nd = S.inodes + 8 * (size_t)node;
-    float4 ax, ay, az, bx, by, bz, rf, pad;
-    ldg8(nd, ax, ay);
-    ldg8(nd + 2, az, bx);
-    ldg8(nd + 4, by, bz);
-    ldg8(nd + 6, rf, pad);
+    const float4* nd = S.inodes + 4 * (size_t)node;
+    float4 q0, q1, q2, q3;
+    ldg8(nd, q0, q1);
+    ldg8(nd + 2, q2, q3);
+    // q0 = min.x[0..3] min.y[0..3] ; q1 = min.z max.x ; q2 = max.y max.z ; q3 = refs
+    const float2 ax01 = unpack_half2(q0.x), ax23 = unpack_half2(q0.y), ay01 = unpack_half2(q0.z), ay23 = unpack_half2(q0.w);
+    const float2 az01 = unpack_half2(q1.x), az23 = unpack_half2(q1.y), bx01 = unpack_half2(q1.z), bx23 = unpack_half2(q1.w);
+    const float2 by01 = unpack_half2(q2.x), by23 = unpack_half2(q2.y), bz01 = unpack_half2(q2.z), bz23 = unpack_half2(q2.w);
     NodeVisit v;
-    v.ref[0] = __float_as_uint(rf.x); v.ref[1] = __float_as_uint(rf.y);
-    v.ref[2] = __float_as_uint(rf.z); v.ref[3] = __float_as_uint(rf.w);
-    slab(ax.x, ay.x, az.x, bx.x, by.x, bz.x, inv, oi, v.ref[0], v.hit[0], v.tc[0]);
-    slab(ax.y, ay.y, az.y, bx.y, by.y, bz.y, inv, oi, v.ref[1], v.hit[1], v.tc[1]);
-    slab(ax.z, ay.z, az.z, bx.z, by.z, bz.z, inv, oi, v.ref[2], v.hit[2], v.tc[2]);
-    slab(ax.w, ay.w, az.w, bx.w, by.w, bz.w, inv, oi, v.ref[3], v.hit[3], v.tc[3]);
+    v.ref[0] = __float_as_uint(q3.x); v.ref[1] = __float_as_uint(q3.y);
+    v.ref[2] = __float_as_uint(q3.z); v.ref[3] = __float_as_uint(q3.w);
+    float tc;
+    slab(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, v.ref[0], v.hit[0], tc);
+    slab(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, v.ref[1], v.hit[1], tc);
+    slab(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, v.ref[2], v.hit[2], tc);
+    slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, v.ref[3], v.hit[3], tc);
     return v;
 }
 // closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)
 RT_D void leaf_best(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, int& bid, uint32_t* tests) {
-    uint32_t first = ref & 0xFFFFFFu, count = ((ref >> 24) & 0x7Fu) + 1;
+    uint32_t first = ref & 0xFFFFFFu, count = ((ref >> 24) & 0x3Fu) + 1;
     bt = kInfF;
     bid = -1;
     for (uint32_t p = first; p < first + count; ++p) {
@@ -423,6 +433,33 @@ RT_D void leaf_best(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, 
         if (prim_hit_t(S, p, o, d, t) && t < bt) { bt = t; bid = (int)p; }
     }
     if (tests) *tests += count;
+}
+
+// One candidate leaf: the EXACT box of the reference leaf first (a single untransformed triangle
+// has min/max of its vertices as its reference AABB, src/bvh.cpp:53-64; other leaves keep theirs in
+// ubox), then its primitives.  Returns false when the ray misses the exact box.
+RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, vec3 inv, vec3 oi, float& bt, int& bid, float& tc,
+                    uint32_t* tests) {
+    const uint32_t first = ref & 0xFFFFFFu;
+    bt = kInfF;
+    bid = -1;
+    bool hitbox;
+    if (ref & IREF_FAST) {
+        float4 g0 = ldg4(S.geo0 + first), g1 = ldg4(S.geo1 + first), g2 = ldg4(S.geo2 + first);
+        slab(fminf(fminf(g0.x, g1.x), g2.x), fminf(fminf(g0.y, g1.y), g2.y), fminf(fminf(g0.z, g1.z), g2.z),
+             fmaxf(fmaxf(g0.x, g1.x), g2.x), fmaxf(fmaxf(g0.y, g1.y), g2.y), fmaxf(fmaxf(g0.z, g1.z), g2.z),
+             inv, oi, ref, hitbox, tc);
+        if (!hitbox) return false;
+        float t; bool interior;
+        if (isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), mk3(g0.w, g1.w, g2.w), t, interior)) { bt = t; bid = (int)first; }
+        if (tests) ++*tests;
+        return true;
+    }
+    float4 bmn = ldg4(S.ubox + 2 * (size_t)first), bmx = ldg4(S.ubox + 2 * (size_t)first + 1);
+    slab(bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z, inv, oi, ref, hitbox, tc);
+    if (!hitbox) return false;
+    leaf_best(S, ref, o, d, bt, bid, tests);
+    return true;
 }
 
 // All reference leaves whose AABB the ray touches, via the index BVH; primitives of a touched
@@ -438,26 +475,16 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
     uint32_t stack[kIndexStack];
     int sp = 0;
     uint32_t ref = S.iroot;
-    float ref_tc = -kInfF;
-    if (ref & IREF_LEAF) {
-        // a single leaf: its box is the reference root box
-        float te; bool interior; uint32_t l, r;
-        if (!ref_box(S, S.root, o, d, te, interior, l, r)) return true;
-        ref_tc = interior ? -kInfF : te;
-    }
     for (;;) {
         if (ref & IREF_LEAF) {
-            float bt; int bid;
-            leaf_best(S, ref, o, d, bt, bid, tests);
-            if (bid >= 0) {
+            float bt, tc; int bid;
+            if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, tests) && bid >= 0) {
                 if (k == kMaxRecords) return false;
-                rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc;
+                rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc;
                 ++k;
             }
             if (sp == 0) break;
-            sp -= 2;
-            ref = stack[sp];
-            ref_tc = __uint_as_float(stack[sp + 1]);
+            ref = stack[--sp];
             continue;
         }
         if (visits) ++*visits;
@@ -466,16 +493,13 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (!v.hit[c]) continue;
-            if (!have) { ref = v.ref[c]; ref_tc = v.tc[c]; have = true; continue; }
-            if (sp + 2 > kIndexStack) return false;
-            stack[sp] = v.ref[c]; stack[sp + 1] = __float_as_uint(v.tc[c]);
-            sp += 2;
+            if (!have) { ref = v.ref[c]; have = true; continue; }
+            if (sp + 1 > kIndexStack) return false;
+            stack[sp++] = v.ref[c];
         }
         if (!have) {
             if (sp == 0) break;
-            sp -= 2;
-            ref = stack[sp];
-            ref_tc = __uint_as_float(stack[sp + 1]);
+            ref = stack[--sp];
         }
     }
     return true;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // idle lanes REFILL from the queue.  Every iteration the warp votes and executes the kind most
 // lanes are ready for, which keeps lanes busy although rays need between one and several
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
-constexpr int kStackWords = 72;  // per lane: inner-node stack from the bottom, noted leaves (2 words) from the top
+constexpr int kStackWords = 56;  // per lane: inner-node stack from the bottom, noted leaves from the top
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kVisitQuorum = 20;  // at least this many lanes ready to visit: skip the full vote
 
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
 
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
-        bool room = sp + 2 * nl + 8 <= kStackWords;
+        bool room = sp + nl + 7 <= kStackWords;
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
         const bool canV = active && node != kNone && room;
         const unsigned mV = __ballot_sync(kFullMask, canV);
@@ -169,8 +169,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
                     const bool leaf = (v.ref[c] & IREF_LEAF) != 0;
                     if (v.hit[c] && leaf) {  // note the leaf, test it later
                         ++nl;
-                        stk[kStackWords - 2 * nl] = v.ref[c];
-                        stk[kStackWords - 2 * nl + 1] = __float_as_uint(v.tc[c]);
+                        stk[kStackWords - nl] = v.ref[c];
                     }
                     const bool inner = v.hit[c] && !leaf;
                     if (inner && next != kNone) { stk[sp] = v.ref[c]; ++sp; }
@@ -183,14 +182,12 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
         } else if (kind == kLeaf) {
             // ---- LEAF: one noted reference leaf per ready lane
             if (canL) {
-                uint32_t ref = stk[kStackWords - 2 * nl];
-                float ref_tc = __uint_as_float(stk[kStackWords - 2 * nl + 1]);
+                const uint32_t ref = stk[kStackWords - nl];
                 --nl;
-                float bt; int bid;
-                leaf_best(S, ref, o, d, bt, bid, STATS ? &tests : nullptr);
-                if (bid >= 0) {
+                float bt, tc; int bid;
+                if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, STATS ? &tests : nullptr) && bid >= 0) {
                     if (k == kMaxRecords) { overflow = true; node = kNone; sp = 0; nl = 0; }
-                    else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = ref_tc; ++k; }
+                    else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc; ++k; }
                 }
             }
         } else if (kind == kFinish) {
@@ -222,14 +219,10 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
                 oi = o * inv;
                 sp = 0; nl = 0; k = 0; overflow = false;
                 active = true;
-                if (S.iroot & IREF_LEAF) {  // single-leaf tree: the leaf box is the reference root box
+                if (S.iroot & IREF_LEAF) {  // single-leaf tree
                     node = kNone;
-                    float te; bool interior; uint32_t l, r;
-                    if (ref_box(S, S.root, o, d, te, interior, l, r)) {
-                        nl = 1;
-                        stk[kStackWords - 2] = S.iroot;
-                        stk[kStackWords - 1] = __float_as_uint(interior ? -kInfF : te);
-                    }
+                    nl = 1;
+                    stk[kStackWords - 1] = S.iroot;
                 } else node = S.iroot;
             }
             pool_base += serve;

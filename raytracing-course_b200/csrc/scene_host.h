@@ -60,7 +60,8 @@ struct FlatScene {
     std::vector<f4> xf_pos;            // (pos.xyz, bits(type|flags))
     std::vector<f4> xf_rot;            // quaternion xyzw
     std::vector<f4> mat0, mat1;        // (col.rgb, bits(material)) (emission.rgb, ior)
-    // index BVH (4-wide, all child boxes in the node): 8 x f4 = 128 bytes per node
+    // index BVH, 4-wide, 64 bytes per node (4 x f4): child boxes as fp16 rounded OUTWARD
+    // (min.x[4] min.y[4] min.z[4] max.x[4] | max.y[4] max.z[4] refs[4]); exact leaf boxes: ubox
     std::vector<f4> inodes;
     uint32_t iroot = 0;  // child reference of the root (may be a leaf reference)
     // reference BVH: 2 x f4 per node (centre.xyz, bits(left)) (half.xyz, bits(right)) + meta
@@ -69,6 +70,7 @@ struct FlatScene {
     // LCA range-min table over cut positions: levels x nbvh entries of node ids
     std::vector<uint32_t> lca;
     uint32_t lca_levels = 0;
+    std::vector<f4> ubox;              // 2 x f4 per primitive slot: (min,0) (max,0) of the reference leaf starting there
     std::vector<f4> planes;            // 2 x f4 per plane: (n, bits(prim id)) (pos, bits(no rotation))
     std::vector<int32_t> lights;
     uint32_t index_depth = 0, ref_depth = 0, units = 0;
@@ -94,7 +96,8 @@ struct HostScene {
 // child reference encoding of the index BVH
 constexpr uint32_t IREF_LEAF = 0x80000000u;
 constexpr uint32_t IREF_NONE = 0xFFFFFFFFu;
-constexpr uint32_t IREF_MAX_LEAF_PRIMS = 128;  // 7 bits
+constexpr uint32_t IREF_FAST = 0x40000000u;     // leaf = one triangle with pos 0 and identity rotation
+constexpr uint32_t IREF_MAX_LEAF_PRIMS = 64;   // 6 bits (24..29)
 constexpr uint32_t IREF_MAX_PRIMS = 1u << 24;
 
 Aabb aabb_of_primitive(const Primitive& p);  // AABB_t::AABB_t(const Primitive&) src/bvh.cpp:41-87

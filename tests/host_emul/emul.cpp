@@ -55,6 +55,7 @@ void* emu_scene_load(const char* path) {
     S.mat0 = (const float4*)F.mat0.data(); S.mat1 = (const float4*)F.mat1.data();
     S.inodes = (const float4*)F.inodes.data(); S.rnodes = (const float4*)F.rnodes.data();
     S.rmeta = (const uint4*)F.rmeta.data(); S.lca = F.lca.data(); S.lights = F.lights.data();
+    S.ubox = (const float4*)F.ubox.data();
     S.planes = (const float4*)F.planes.data(); S.nplanes = (uint32_t)(F.planes.size() / 2);
     S.nprims = (uint32_t)e->host.prims.size(); S.nbvh = e->host.nbvh; S.nnodes = (uint32_t)e->host.nodes.size();
     S.root = e->host.root; S.iroot = F.iroot; S.lca_levels = F.lca_levels; S.nlights = (uint32_t)e->host.lights.size();

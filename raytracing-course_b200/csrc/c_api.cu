@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -53,7 +54,7 @@ struct DevBuf {
     }
 };
 
-constexpr uint64_t kDefaultBatchPaths = 1ull << 23;
+constexpr uint64_t kDefaultBatchPaths = 1ull << 24;
 constexpr int kMaxDepthSlots = 64;
 }  // namespace
 
@@ -70,12 +71,30 @@ struct rtc_scene {
     unsigned char* arena_host = nullptr;  // cudaMallocHost
     size_t arena_bytes = 0;
     DevScene slices{};                    // pointers into arena_dev (scalars filled by dev())
-    // wavefront state
-    DevBuf<float4> path[2][4];
-    DevBuf<float> hit_cd[2];             // ping-pong like the path queues
-    DevBuf<uint32_t> hit_id[2];
-    DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
-    DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
+    // wavefront state: kMaxLanes independent sets, each with its own stream, so that batches
+    // overlap (the tail of one persistent k_traverse launch runs next to the other lane's kernels)
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf<float4> path[2][4];
+        DevBuf<float> hit_cd[2];             // ping-pong like the path queues
+        DevBuf<uint32_t> hit_id[2];
+        DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
+        DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
+        void release() {
+            for (auto& set : path) for (auto& b : set) b.release();
+            for (auto& b : hit_cd) b.release();
+            for (auto& b : hit_id) b.release();
+            trav_queue.release(); queue.release();
+            if (done) cudaEventDestroy(done);
+            if (stream) cudaStreamDestroy(stream);
+            done = nullptr; stream = nullptr;
+        }
+    };
+    static constexpr int kMaxLanes = 4;
+    Lane lanes[kMaxLanes];
+    int nlanes = 2;                      // env RTC_STREAMS (1..4)
+    cudaEvent_t fork = nullptr;
     DevBuf<unsigned long long> stats;    // 8 words
     DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
     DevBuf<uint8_t> rgb;
@@ -146,10 +165,10 @@ struct rtc_scene {
         if (arena_host) cudaFreeHost(arena_host);
         arena_dev = arena_host = nullptr;
         arena_bytes = 0;
-        for (auto& set : path) for (auto& b : set) b.release();
-        for (auto& b : hit_cd) b.release();
-        for (auto& b : hit_id) b.release();
-        trav_queue.release(); queue.release(); stats.release(); accum.release(); rgb.release();
+        for (auto& l : lanes) l.release();
+        if (fork) cudaEventDestroy(fork);
+        fork = nullptr;
+        stats.release(); accum.release(); rgb.release();
         collect_spans();
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
         event_pool.clear();
@@ -202,7 +221,6 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
     CU(cudaMemcpyAsync(s->arena_dev, s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, nullptr));
     CU(cudaStreamSynchronize(nullptr));
     const uint64_t bytes = payload;
-    CU(s->queue.ensure(3 * kMaxDepthSlots));
     if (!s->stats.p) {
         CU(s->stats.ensure(8));
         CU(cudaMemset(s->stats.p, 0, 8 * sizeof(unsigned long long)));
@@ -231,6 +249,10 @@ rtc_scene* make_scene(const std::string& text, int device) {
         fail(RTC_ERR_UNSUPPORTED, "reference BVH deeper than 95 levels is not supported");
         delete s;
         return nullptr;
+    }
+    if (const char* v = std::getenv("RTC_STREAMS")) {
+        int n = std::atoi(v);
+        s->nlanes = n < 1 ? 1 : (n > rtc_scene::kMaxLanes ? rtc_scene::kMaxLanes : n);
     }
     s->device = device;
     if (device >= 0) {
@@ -282,11 +304,18 @@ struct Staged {
 };
 #define NEED(ptr) if (!(ptr)) return fail(RTC_ERR_CUDA, "device staging allocation/copy failed")
 
-int ensure_wavefront(rtc_scene* s, uint64_t cap) {
-    for (auto& set : s->path) for (auto& b : set) CU(b.ensure(cap));
-    for (auto& b : s->hit_cd) CU(b.ensure(cap));
-    for (auto& b : s->hit_id) CU(b.ensure(cap));
-    CU(s->trav_queue.ensure(cap));
+int ensure_wavefront(rtc_scene* s, uint64_t cap, int nlanes) {
+    if (!s->fork) CU(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+    for (int i = 0; i < nlanes; ++i) {
+        rtc_scene::Lane& l = s->lanes[i];
+        if (!l.stream) CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        if (!l.done) CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        for (auto& set : l.path) for (auto& b : set) CU(b.ensure(cap));
+        for (auto& b : l.hit_cd) CU(b.ensure(cap));
+        for (auto& b : l.hit_id) CU(b.ensure(cap));
+        CU(l.trav_queue.ensure(cap));
+        CU(l.queue.ensure(3 * kMaxDepthSlots));
+    }
     return RTC_OK;
 }
 
@@ -519,38 +548,58 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     const uint64_t total = npix * sample_count;
     if (total == 0) return RTC_OK;
     const uint32_t depth = s->host.ray_depth;
-    const uint64_t cap = total < s->batch_paths ? total : s->batch_paths;
-    if ((rc = ensure_wavefront(s, cap))) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    LaunchCtx c{st, s->sms};
+    // batch size: the configured one, but small enough that every lane gets a batch (overlap matters
+    // more than batch size: profiles/r01_experiments.md), rounded up to whole warps
+    uint64_t cap = total < s->batch_paths ? total : s->batch_paths;
+    if (!s->profiling && s->nlanes > 1) {
+        uint64_t per_lane = ((total + s->nlanes - 1) / s->nlanes + 31) & ~(uint64_t)31;
+        if (per_lane < cap) cap = per_lane;
+    }
+    const uint64_t nbatches = (total + cap - 1) / cap;
+    // per-kernel event timing needs the kernels back to back on one stream
+    const int nlanes = s->profiling ? 1 : (int)(nbatches < (uint64_t)s->nlanes ? nbatches : (uint64_t)s->nlanes);
+    if ((rc = ensure_wavefront(s, cap, nlanes))) return rc;
+    cudaStream_t user = (cudaStream_t)stream;
     DevScene S = s->dev();
-    uint32_t* tqc = s->queue.p + kMaxDepthSlots;        // rays queued for k_traverse, per bounce
-    uint32_t* cursor = s->queue.p + 2 * kMaxDepthSlots; // k_traverse work cursors, per bounce
-    for (uint64_t first = 0; first < total; first += cap) {
+    // fork: the lane streams start after everything already queued on the caller's stream
+    CU(cudaEventRecord(s->fork, user));
+    for (int i = 0; i < nlanes; ++i) CU(cudaStreamWaitEvent(s->lanes[i].stream, s->fork, 0));
+    uint64_t batch = 0;
+    for (uint64_t first = 0; first < total; first += cap, ++batch) {
+        rtc_scene::Lane& L = s->lanes[batch % nlanes];
+        cudaStream_t st = L.stream;
+        LaunchCtx c{st, s->sms};
+        uint32_t* tqc = L.queue.p + kMaxDepthSlots;        // rays queued for k_traverse, per bounce
+        uint32_t* cursor = L.queue.p + 2 * kMaxDepthSlots; // k_traverse work cursors, per bounce
         uint32_t count = (uint32_t)((total - first) < cap ? (total - first) : cap);
-        CU(cudaMemsetAsync(s->queue.p, 0, 3 * kMaxDepthSlots * sizeof(uint32_t), st));
-        PathSoA cur{s->path[0][0].p, s->path[0][1].p, s->path[0][2].p, s->path[0][3].p};
-        PathSoA nxt{s->path[1][0].p, s->path[1][1].p, s->path[1][2].p, s->path[1][3].p};
-        HitSoA hcur{s->hit_cd[0].p, s->hit_id[0].p}, hnxt{s->hit_cd[1].p, s->hit_id[1].p};
+        CU(cudaMemsetAsync(L.queue.p, 0, 3 * kMaxDepthSlots * sizeof(uint32_t), st));
+        PathSoA cur{L.path[0][0].p, L.path[0][1].p, L.path[0][2].p, L.path[0][3].p};
+        PathSoA nxt{L.path[1][0].p, L.path[1][1].p, L.path[1][2].p, L.path[1][3].p};
+        HitSoA hcur{L.hit_cd[0].p, L.hit_id[0].p}, hnxt{L.hit_cd[1].p, L.hit_id[1].p};
         s->span_begin(0, st);
-        launch_generate(c, S, cur, hcur, s->queue.p, s->trav_queue.p, tqc, first, count, seed, sample_begin);
+        launch_generate(c, S, cur, hcur, L.queue.p, L.trav_queue.p, tqc, first, count, seed, sample_begin);
         s->span_end(st);
         s->launches++;
         for (uint32_t b = 1; b <= depth; ++b) {
             s->span_begin(1, st);
-            if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, s->queue.p + (b - 1), count);
-            else launch_traverse(c, S, cur, hcur, count, s->trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
+            if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, L.queue.p + (b - 1), count);
+            else launch_traverse(c, S, cur, hcur, count, L.trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
             s->span_end(st);
             s->span_begin(2, st);
-            launch_shade(c, S, cur, hcur, nxt, hnxt, s->queue.p + (b - 1), s->queue.p + b, s->trav_queue.p, tqc + b, count,
+            launch_shade(c, S, cur, hcur, nxt, hnxt, L.queue.p + (b - 1), L.queue.p + b, L.trav_queue.p, tqc + b, count,
                          accum_dev, b, seed);
             s->span_end(st);
             s->launches += 2;
             PathSoA tmp = cur; cur = nxt; nxt = tmp;
             HitSoA htmp = hcur; hcur = hnxt; hnxt = htmp;
         }
-        launch_tally(c, s->queue.p, tqc, depth, s->stats.p);
+        launch_tally(c, L.queue.p, tqc, depth, s->stats.p);
         s->launches++;
+    }
+    // join: the caller's stream continues when every lane is done
+    for (int i = 0; i < nlanes; ++i) {
+        CU(cudaEventRecord(s->lanes[i].done, s->lanes[i].stream));
+        CU(cudaStreamWaitEvent(user, s->lanes[i].done, 0));
     }
     CU(cudaGetLastError());
     return RTC_OK;

@@ -261,7 +261,11 @@ RT_D void deposit(float* accum, uint32_t pixel, vec3 L) {
 // Scene::RayTrace's material switch (src/scene.cpp:96-177) for one bounce, recursion unrolled:
 // L = sum_k beta_k * E_k.  Surviving paths are written compacted (warp ballot + one atomic per
 // warp) into the next queue; finished paths add their radiance to the pixel sum.
-__global__ void __launch_bounds__(256) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
+#ifndef RTC_SHADE_THREADS
+#define RTC_SHADE_THREADS 128   // 128 x 6 blocks/SM (80 registers, 76 B spills) measured best: profiles/r01_experiments.md
+#define RTC_SHADE_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                                                 uint32_t* qout, uint32_t* tq, uint32_t* tq_count, float* accum, uint32_t bounce,
                                                 uint32_t seed) {
     const uint32_t count = *qin;
@@ -491,7 +495,7 @@ void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, Hit
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                   uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float* accum, uint32_t bounce,
                   uint32_t seed) {
-    k_shade<<<grid_for(max_count, 256, c.sms, 8), 256, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
+    k_shade<<<grid_for(max_count, RTC_SHADE_THREADS, c.sms, 2048 / RTC_SHADE_THREADS), RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
 }
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     k_tally<<<1, 1, 0, c.stream>>>(q, tqc, ray_depth, stats);

@@ -10,7 +10,7 @@ STRONG: the total work per step is fixed.
                (+ the NCCL reduce for N > 1), CUDA events, max over ranks.
   e2e          same metric through the C-ABI with host buffers: every step re-uploads the
                flattened scene (H2D), renders, resolves to 8-bit and copies the image back (D2H).
-  roofline     dominant kernel = k_extend (Scene::RayIntersection); see DESIGN.md "Roofline".
+  roofline     dominant kernel (k_traverse = BVH part of Scene::RayIntersection); see DESIGN.md "Roofline".
   cpu_baseline the UNMODIFIED reference (oracle/_ref/librefprobe.so -> Scene::Sample loop) on the
                host cores, on a bounded sample of the same scene.
 
@@ -278,7 +278,7 @@ def main():
         tests_per_ray = stats["prim_tests"] / max(stats["traversed_rays"], 1)
         planes = scene.nprims - scene.nbvh
         alg = {  # (bytes per unit, units processed in the timed region, kernel)
-            "traverse": (4 + 32 + 4 + 4 + 112 * visits_per_ray + 48 * tests_per_ray, trav0,
+            "traverse": (4 + 32 + 4 + 4 + 64 * visits_per_ray + 48 * tests_per_ray, trav0,
                          "k_traverse" if args.traversal == 0 else "k_extend_reftree"),
             "pre": (32 + 8 + 64 + 32 * planes + 4 * (trav0 / rays0), rays0, "k_pre"),
             "shade": (64 + 4 + 48 + 32 + 64 + 12, rays0, "k_shade"),
@@ -291,8 +291,15 @@ def main():
         peak, peak_src = measured_peaks()
         achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         kernel_ms = {k: v["ms"] / args.steps for k, v in prof.items()}
+        traffic = None  # DRAM bytes per launch of that kernel from the committed ncu pass (profiles/)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("workload") == args.scene and kname in tj.get("kernels", {}):
+                traffic = tj["kernels"][kname]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_unit": bytes_per_unit, "unit_name": "ray entering the BVH" if top == "traverse" else "ray",
                     "units_per_launch": units / launches,
                     "index_node_visits_per_traversed_ray": visits_per_ray, "prim_tests_per_traversed_ray": tests_per_ray,

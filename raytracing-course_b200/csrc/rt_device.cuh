@@ -520,8 +520,12 @@ RT_D void closest_plane(const DevScene& S, vec3 o, vec3 d, float& closest, int& 
             vec3 n = ld3(a);
             t = -dot(o - ld3(b), n) / dot(d, n);
             ok = t > 0.f && !(t > 1e5f);
-        } else {
-            ok = prim_hit_t(S, prim, o, d, t);
+        } else {  // rotated plane: ray into the plane's frame (src/primitives.cpp:15), plane code only
+            vec3 lo = o, ld = d;
+            to_local(S, prim, prim_flags(S, prim), lo, ld);
+            Isect is;
+            ok = isect_plane(lo, ld, ld3(a), is);
+            t = is.t;
         }
         if (ok && t < closest) { closest = t; id = (int)prim; }
     }
@@ -562,6 +566,24 @@ RT_D SceneHit scene_intersect(const DevScene& S, vec3 o, vec3 d, uint32_t* visit
     return h;
 }
 
+// Primitive::Intersect restricted to what a light can be (box or ellipsoid): same arithmetic as
+// prim_intersect<true>, without the triangle / plane code (k_shade is instruction-cache bound).
+RT_D bool light_intersect(const DevScene& S, uint32_t prim, bool is_box, vec3 o, vec3 d, Isect& out) {
+    uint32_t flags = prim_flags(S, prim);
+    to_local(S, prim, flags, o, d);
+    vec3 g0 = ld3(ldg4(S.geo0 + prim));
+    bool ok = is_box ? isect_box<true>(o, d, g0, out) : isect_ellipsoid(o, d, g0, out);
+    if (!ok) return false;
+    if (!(flags & PF_ROT_IDENT)) {
+        float4 q4 = ldg4(S.xf_rot + prim);
+        quat q;
+        q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
+        out.n = rotate(q, out.n);
+    }
+    out.n = rt_normalize<true>(out.n);
+    return true;
+}
+
 // ------------------------------------------------------------------------------- distributions
 // Distribution::SampleCosine, src/distributions.cpp:144-159
 RT_D vec3 sample_cosine(const Rng& g, vec3 n) {
@@ -590,8 +612,8 @@ RT_D vec3 sample_box(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
         else pnt.z = side * s.z;
         vec3 on_box = rotate(q, pnt) + pos;
         smp = normalize(on_box - x);
-        float t;
-        if (prim_hit_t<true>(S, prim, x, smp, t)) break;
+        Isect is;
+        if (light_intersect(S, prim, true, x, smp, is)) break;
     }
     return smp;
 }
@@ -606,8 +628,8 @@ RT_D vec3 sample_ellipsoid(const DevScene& S, uint32_t prim, const Rng& g, vec3 
         vec3 k = normal_vec(g.block(2 + 2 * j));
         vec3 on = rotate(q, r * k) + pos;
         smp = normalize(on - x);
-        float t;
-        if (prim_hit_t<true>(S, prim, x, smp, t)) break;
+        Isect is;
+        if (light_intersect(S, prim, false, x, smp, is)) break;
     }
     return smp;
 }
@@ -641,14 +663,14 @@ RT_D float pdf_point(const DevScene& S, uint32_t prim, bool is_box, float dist2,
 RT_D float pdf_light(const DevScene& S, uint32_t prim, vec3 x, vec3 d) {
     bool is_box = (prim_flags(S, prim) & PF_TYPE_MASK) == PT_BOX;
     Isect i1;
-    if (!prim_intersect<true>(S, prim, x, d, i1)) return 1e-9f;
+    if (!light_intersect(S, prim, is_box, x, d, i1)) return 1e-9f;
     if (i1.t <= 1e-8f) return 1e-9f;
     vec3 p1 = x + i1.t * d;
     vec3 v1 = p1 - x;
     float sum = pdf_point(S, prim, is_box, dot(v1, v1), p1, i1.n, d);
     float step = i1.t + 1e-4f;
     Isect i2;
-    if (prim_intersect<true>(S, prim, x + step * d, d, i2)) {
+    if (light_intersect(S, prim, is_box, x + step * d, d, i2)) {
         float t2 = i2.t + step;
         vec3 p2 = x + t2 * d;
         vec3 v2 = p2 - x;

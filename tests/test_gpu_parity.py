@@ -261,3 +261,78 @@ def test_full_size_properties_dragon_100k(rtc, gpu_scenes):
     assert np.allclose(a[ok], b[ok], rtol=1e-4, atol=1e-5)
     assert (a[ok] >= 0).all()
     s.override(samples=128)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: scenes built in the test, compared with the oracle on the same text
+EDGE_SCENES = {
+    "planes_only": "DIMENSIONS 33 17\nSAMPLES 3\nRAY_DEPTH 4\nBG_COLOR 0.2 0.3 0.4\nCAMERA_POSITION 0 1 3\nCAMERA_RIGHT 1 0 0\nCAMERA_UP 0 1 0\n"
+                   "CAMERA_FORWARD 0 0 -1\nCAMERA_FOV_X 1.2\nNEW_PRIMITIVE\nPLANE 0 1 0\nCOLOR 0.8 0.8 0.8\nNEW_PRIMITIVE\nPLANE 0 0 1\n"
+                   "POSITION 0 0 -3\nROTATION 0 0.1736482 0 0.9848078\nCOLOR 0.9 0.2 0.2\nEMISSION 0.5 0.5 0.5\n",
+    "one_sample_depth_one": "DIMENSIONS 31 9\nSAMPLES 1\nRAY_DEPTH 1\nBG_COLOR 1 1 1\nCAMERA_POSITION 0 0 4\nCAMERA_RIGHT 1 0 0\nCAMERA_UP 0 1 0\n"
+                            "CAMERA_FORWARD 0 0 -1\nCAMERA_FOV_X 1.0\nNEW_PRIMITIVE\nELLIPSOID 1 0.5 0.7\nCOLOR 0.5 0.6 0.7\nEMISSION 0.1 0.2 0.3\n",
+    # five identical overlapping ellipsoids: the SAH refuses to split them -> one reference leaf with 5 primitives
+    "multi_primitive_leaf": "DIMENSIONS 40 30\nSAMPLES 4\nRAY_DEPTH 5\nBG_COLOR 0.1 0.1 0.1\nCAMERA_POSITION 0 0 5\nCAMERA_RIGHT 1 0 0\nCAMERA_UP 0 1 0\n"
+                            "CAMERA_FORWARD 0 0 -1\nCAMERA_FOV_X 1.0\n" +
+                            "".join("NEW_PRIMITIVE\nELLIPSOID 1 1 1\nPOSITION 0 0 0\nCOLOR 0.%d 0.5 0.5\n\n" % (i + 2) for i in range(5)) +
+                            "NEW_PRIMITIVE\nBOX 0.3 0.3 0.3\nPOSITION 2 0 0\nEMISSION 5 5 5\n\nNEW_PRIMITIVE\nPLANE 0 1 0\nPOSITION 0 -1 0\nCOLOR 0.7 0.7 0.7\n",
+    # glass ball in front of a metal box and a rotated emissive ellipsoid: deep specular chains
+    "specular_chain": "DIMENSIONS 48 32\nSAMPLES 6\nRAY_DEPTH 12\nBG_COLOR 0.3 0.4 0.5\nCAMERA_POSITION 0 1 5\nCAMERA_RIGHT 1 0 0\nCAMERA_UP 0 1 0\n"
+                      "CAMERA_FORWARD 0 0 -1\nCAMERA_FOV_X 1.1\nNEW_PRIMITIVE\nELLIPSOID 0.9 0.9 0.9\nPOSITION 0 1 0\nDIELECTRIC\nIOR 1.33\nCOLOR 0.9 1 0.9\n\n"
+                      "NEW_PRIMITIVE\nBOX 3 2 0.1\nPOSITION 0 1 -2\nROTATION 0 0.0871557 0 0.9961947\nMETALLIC\nCOLOR 0.9 0.9 0.9\n\n"
+                      "NEW_PRIMITIVE\nELLIPSOID 0.3 0.2 0.3\nPOSITION 2 3 1\nROTATION 0.2 0.1 0 0.9746794\nEMISSION 8 7 6\n\n"
+                      "NEW_PRIMITIVE\nPLANE 0 1 0\nCOLOR 0.6 0.6 0.6\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_SCENES))
+def test_edge_scenes_vs_oracle(rtc, oracle_lib, name):
+    text = EDGE_SCENES[name]
+    s = rtc.Scene(text=text, device=0)
+    raw = text.encode()
+    h = oracle_lib.lib.orc_scene_parse(raw, len(raw))
+    a = orclib.Scene.__new__(orclib.Scene)
+    a.b, a.h = oracle_lib, h
+    info = np.zeros(8, np.uint32)
+    oracle_lib.lib.orc_scene_info(h, info)
+    (a.width, a.height, a.ray_depth, a.samples, a.nprims, a.nbvh, a.nnodes, a.nlights) = [int(v) for v in info]
+    assert [s.width, s.height, s.ray_depth, s.samples, s.nprims, s.nbvh, s.nnodes, s.nlights] == info.tolist()
+    # primary hits, both traversal modes
+    ys, xs = np.mgrid[0:s.height, 0:s.width]
+    xy = np.stack([xs.ravel() + 0.5, ys.ravel() + 0.5], 1).astype(np.float32)
+    o, d = s.cam.GetToRay(xy)
+    want = a.intersect(o, d)
+    check_hits(s.RayIntersection(o, d, rtc.TRAVERSAL_INDEX), want, id_agree=0.998)
+    check_hits(s.RayIntersection(o, d, rtc.TRAVERSAL_REFTREE), want, id_agree=0.998)
+    # render with the same Philox streams
+    got = s.RenderSum(seed=4, sample_count=s.samples).reshape(-1, 3)
+    ref, paths, rays = a.render_sum(4, 0, s.samples)
+    c = s.counters()
+    assert c["paths"] == paths
+    # deep specular chains amplify rounding differences (total-internal-reflection thresholds, Fresnel
+    # coin flips): path lengths then differ on a fraction of a percent of the paths
+    chaotic = name == "specular_chain"
+    assert abs(c["rays"] - rays) <= (1e-2 if chaotic else 2e-3) * rays + 2
+    ok = np.isfinite(ref).all(1) & np.isfinite(got).all(1)
+    rel = np.abs(got - ref).max(1) / (np.abs(ref).max(1) + 1e-3)
+    assert ((rel <= 2e-3) & ok).mean() >= (0.9 if chaotic else 0.98), ((rel <= 2e-3) & ok).mean()
+    img = s.Render(seed=4)
+    assert img.shape == (s.height, s.width, 3)
+    a.close()
+    s.close()
+
+
+def test_large_frame_4k(rtc, gpu_scenes):
+    """BASELINE configs[4] geometry at reduced spp: 3840x2160 of the metal dragon, 2 spp (16.6 M paths)."""
+    s = rtc.Scene(path=scene_path("practice5_dragon_100k_metal"), device=0)
+    s.override(3840, 2160, 2)
+    s.reset_counters()
+    a = s.RenderSum(seed=1, sample_count=2)
+    c = s.counters()
+    assert c["paths"] == 3840 * 2160 * 2
+    assert a.shape == (2160, 3840, 3)
+    ok = np.isfinite(a)
+    assert ok.mean() > 0.9999 and (a[ok] >= 0).all() and a[ok].max() > 0
+    img = s.Render(seed=1)
+    assert img.shape == (2160, 3840, 3) and img.max() > 0
+    s.close()

@@ -134,3 +134,12 @@ def test_cli_without_gpu_fails_loudly(rtc):
 def test_host_philox_known_answer(rtc):
     out = rtc.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])
     assert out.tolist() == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_unsupported_scene_is_refused_with_a_message(rtc):
+    """More than 64 primitives in one reference BVH leaf (70 coincident ellipsoids) exceeds a documented limit."""
+    text = "DIMENSIONS 4 4\nSAMPLES 1\nRAY_DEPTH 1\n" + "NEW_PRIMITIVE\nELLIPSOID 1 1 1\nPOSITION 0 0 0\n\n" * 70
+    with pytest.raises(rtc.RtcError, match="more than 64 primitives"):
+        rtc.Scene(text=text, device=-1)
+    with pytest.raises(rtc.RtcError, match="RAY_DEPTH"):
+        rtc.Scene(text="DIMENSIONS 4 4\nRAY_DEPTH 100\nNEW_PRIMITIVE\nBOX 1 1 1\n", device=-1)

@@ -130,11 +130,44 @@ def sort_fixture():
     print("sort fixture done")
 
 
+PARSER_TEXTS = [
+    # attributes given BEFORE the shape line are reset by it; the block ends at the blank line
+    "DIMENSIONS 8 4\nSAMPLES 2\nRAY_DEPTH 3\nNEW_PRIMITIVE\nCOLOR 1 0 0\nIOR 9\nBOX 1 2 3\nPOSITION 1 2 3\nIOR 1.5\n\nNEW_PRIMITIVE\nPLANE 0 1 0\nPOSITION 0 0 0\nMETALLIC\n",
+    # blocks back to back without blank lines; scene commands after a block lose their arguments
+    "DIMENSIONS 4 4\nSAMPLES 3\nRAY_DEPTH 2\nNEW_PRIMITIVE\nELLIPSOID 1 1 1\nPOSITION 0 0 0\nNEW_PRIMITIVE\nTRIANGLE 0 0 0 1 0 0 0 1 0\nPOSITION 0 0 1\nEMISSION 1 1 1\nSAMPLES 9\nRAY_DEPTH 4\n",
+    # unknown words, a stray attribute at scene level, trailing spaces, tabs, no trailing newline
+    "FOO 1 2\nCOLOR 1 1 1\nDIMENSIONS 3 5  \nBG_COLOR 0.1 0.2 0.3\nCAMERA_FOV_X\t1.0\nSAMPLES 1\nRAY_DEPTH 1\nNEW_PRIMITIVE\nBOX 1 1 1\nPOSITION 0 0 0\nROTATION 0 0 0.7071068 0.7071068\nDIELECTRIC",
+    # numbers in exponent / signed form, too few arguments (the rest stays as it was), extra arguments
+    "DIMENSIONS 2 2\nSAMPLES 1\nRAY_DEPTH 1\nNEW_PRIMITIVE\nELLIPSOID 1e0 +2 .5\nPOSITION -1e-1 2\nCOLOR 0.5 0.25 0.125 7 7\n\nNEW_PRIMITIVE\nBOX 1 1\nPOSITION 0 0 0\n",
+]
+
+
+def parser_fixture():
+    """What the reference's Scene::Load makes of unusual inputs (every primitive carries a POSITION:
+    the reference leaves Primitive::pos uninitialised otherwise)."""
+    import tempfile
+    out = {}
+    for i, text in enumerate(PARSER_TEXTS):
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False, newline="") as f:
+            f.write(text)
+        s = orclib.Scene(orclib.ref(), f.name)
+        tm, data = s.prims()
+        out["text%d" % i] = np.frombuffer(text.encode(), np.uint8)
+        out["info%d" % i] = np.array([s.width, s.height, s.ray_depth, s.samples, s.nprims, s.nbvh, s.nnodes, s.nlights])
+        out["tm%d" % i] = tm
+        out["data%d" % i] = data
+        s.close()
+        os.unlink(f.name)
+    np.savez_compressed(os.path.join(GOLD, "parser_quirks.npz"), **out)
+    print("parser fixture:", len(PARSER_TEXTS), "texts")
+
+
 def main():
     if not orclib.have_ref():
         raise SystemExit("oracle/_ref/librefprobe.so missing: run `make -C oracle` where /root/reference exists")
     os.makedirs(GOLD, exist_ok=True)
     sort_fixture()
+    parser_fixture()
     tonemap_fixture()
     primitive_fixture()
     rays_fixture("practice5_1", 8, 1)

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
 
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
+        // a ray without a single hit needs no FINISH step: nothing to replay, nothing to store
+        if (active && node == kNone && nl == 0 && k == 0 && !overflow) active = false;
         bool room = sp + nl + 7 <= kStackWords;
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
         const bool canV = active && node != kNone && room;

@@ -111,7 +111,13 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
 constexpr int kStackWords = 56;  // per lane: inner-node stack from the bottom, noted leaves from the top
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kVisitQuorum = 20;  // at least this many lanes ready to visit: skip the full vote
+#ifndef RTC_LEAF_FIRST
+#define RTC_LEAF_FIRST 8
+#endif
+#ifndef RTC_VISIT_QUORUM
+#define RTC_VISIT_QUORUM 14   // sweep on B200: 10: 23.6, 12: 22.6, 14: 22.4, 16: 23.0, 20: 23.5 ms/step
+#endif
+constexpr int kVisitQuorum = RTC_VISIT_QUORUM;  // at least this many lanes ready to visit: skip the full vote
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
@@ -132,8 +138,6 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
 
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
-        // a ray without a single hit needs no FINISH step: nothing to replay, nothing to store
-        if (active && node == kNone && nl == 0 && k == 0 && !overflow) active = false;
         bool room = sp + nl + 7 <= kStackWords;
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
         const bool canV = active && node != kNone && room;
@@ -152,6 +156,10 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
             if (!(mV | mL | mF | mR)) break;
             const int nL = __popc(mL), nF = __popc(mF);
             nR = __popc(mR);
+            // lanes holding noted leaves are served before the plain majority vote once there are enough
+            // of them (threshold swept on B200: profiles/r01_experiments.md)
+            if (nL >= RTC_LEAF_FIRST) kind = kLeaf;
+            else
             if (nV >= nL && nV >= nF && nV >= nR) kind = kVisit;
             else if (nL >= nF && nL >= nR) kind = kLeaf;
             else if (nF >= nR) kind = kFinish;

@@ -166,6 +166,20 @@ RT_D bool isect_triangle(vec3 o, vec3 d, vec3 a, vec3 b, vec3 c, vec3 n, float& 
     return true;
 }
 
+// glm's quaternion * vector (vecmath.h rotate) without FMA contraction: rotated primitives then see
+// bit-identical local rays to the reference's, which matters for grazing ellipsoid hits (the
+// discriminant b^2 - 4ac cancels, so ulps in the rotated ray become 1e-3 in t).
+RT_D vec3 cross_exact(vec3 a, vec3 b) {
+    return mk3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(b.y, a.z)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(b.z, a.x)),
+               __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(b.x, a.y)));
+}
+RT_D vec3 rotate_exact(quat q, vec3 v) {
+    vec3 qv = mk3(q.x, q.y, q.z);
+    vec3 uv = cross_exact(qv, v);
+    vec3 uuv = cross_exact(qv, uv);
+    vec3 s = mk3(__fadd_rn(__fmul_rn(uv.x, q.w), uuv.x), __fadd_rn(__fmul_rn(uv.y, q.w), uuv.y), __fadd_rn(__fmul_rn(uv.z, q.w), uuv.z));
+    return mk3(__fadd_rn(v.x, __fmul_rn(s.x, 2.0f)), __fadd_rn(v.y, __fmul_rn(s.y, 2.0f)), __fadd_rn(v.z, __fmul_rn(s.z, 2.0f)));
+}
 // Ray into the primitive's local frame: rotate(conjugate(rotator), ray + -1*pos), src/primitives.cpp:15
 RT_D void to_local(const DevScene& S, uint32_t prim, uint32_t flags, vec3& o, vec3& d) {
     if (flags & PF_IDENT) return;
@@ -175,8 +189,8 @@ RT_D void to_local(const DevScene& S, uint32_t prim, uint32_t flags, vec3& o, ve
     float4 q4 = ldg4(S.xf_rot + prim);
     quat qc;
     qc.x = -q4.x; qc.y = -q4.y; qc.z = -q4.z; qc.w = q4.w;
-    o = rotate(qc, o);
-    d = rotate(qc, d);
+    o = rotate_exact(qc, o);
+    d = rotate_exact(qc, d);
 }
 RT_D uint32_t prim_flags(const DevScene& S, uint32_t prim) { return __float_as_uint(__ldg(&S.xf_pos[prim].w)); }
 
@@ -227,7 +241,7 @@ RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect
         float4 q4 = ldg4(S.xf_rot + prim);
         quat q;
         q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
-        out.n = rotate(q, out.n);
+        out.n = rotate_exact(q, out.n);
     }
     out.n = rt_normalize<FAST>(out.n);
     return true;

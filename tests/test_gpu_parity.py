@@ -16,7 +16,7 @@ from conftest import golden, scene_path
 
 pytestmark = pytest.mark.gpu
 
-RAY_SCENES = ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k"]
+RAY_SCENES = ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k", "rabbid"]
 ID_AGREE = 0.999
 T_REL = 1e-4
 
@@ -152,7 +152,7 @@ def squash(x):
 
 @pytest.mark.parametrize("name,w,h,spp", [("practice5_1", 64, 48, 4), ("practice5_2", 64, 48, 8), ("lights_mix", 96, 64, 8),
                                           ("practice5_dragon_10k", 64, 64, 4), ("practice5_dragon_100k_glass", 40, 40, 2),
-                                          ("practice5_dragon_100k_metal", 40, 40, 2), ("practice5_dragon_100k_glow", 40, 40, 2)])
+                                          ("practice5_dragon_100k_metal", 40, 40, 2), ("practice5_dragon_100k_glow", 40, 40, 2), ("rabbid", 88, 88, 4)])
 def test_render_sample_exact_vs_oracle(rtc, oracle_lib, name, w, h, spp):
     """Same Philox streams on both sides: per-pixel radiance sums agree to float rounding except
     where a path crosses a discontinuity differently (a handful of pixels)."""
@@ -180,7 +180,7 @@ def test_render_sample_exact_vs_oracle(rtc, oracle_lib, name, w, h, spp):
 
 
 @pytest.mark.parametrize("name,w,h,spp", [("practice5_1", 64, 48, 256), ("practice5_2", 64, 48, 1024), ("lights_mix", 48, 32, 1024),
-                                          ("practice5_dragon_10k", 64, 64, 256), ("practice5_dragon_10k", 128, 128, 512)])
+                                          ("practice5_dragon_10k", 64, 64, 256), ("practice5_dragon_10k", 128, 128, 512), ("rabbid", 88, 88, 256)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_render_statistically_matches_reference(rtc, name, w, h, spp, mode):
     """Converged-image criterion: against the REFERENCE's own render (its minstd streams).  The

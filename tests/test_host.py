@@ -11,7 +11,7 @@ import pytest
 import orclib
 from conftest import ROOT, golden, scene_path
 
-SCENES = ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k", "practice5_dragon_100k"]
+SCENES = ["practice5_1", "practice5_2", "lights_mix", "rabbid", "practice5_dragon_10k", "practice5_dragon_100k"]
 
 
 def test_library_exports_every_declared_symbol(rtc):

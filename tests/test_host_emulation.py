@@ -48,7 +48,7 @@ def emu_intersect(L, h, o, d, mode):
     return pid, t, nrm, inter, st
 
 
-@pytest.mark.parametrize("name", ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k"])
+@pytest.mark.parametrize("name", ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k", "rabbid"])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_traversal_matches_reference_golden(emu, name, mode):
     g = golden(name + "_rays")

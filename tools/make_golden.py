@@ -41,7 +41,9 @@ def rays_fixture(name, stride, seed):
     spid, st, snrm, sinter = s.intersect(so, sd)
     # random rays: origins in a box around the camera/scene, directions uniform
     lo, hi = (-4.5, -4.5, -4.5), (4.5, 4.5, 14.0)
-    if name.startswith("practice5_1") or name.startswith("practice5_2") or name == "lights_mix":
+    if name == "rabbid":
+        lo, hi = (-5, -8, -8), (5, 4, 3.4)
+    elif name.startswith("practice5_1") or name.startswith("practice5_2") or name == "lights_mix":
         lo, hi = (-6, 0.05, -9), (6, 5, 6)
     ro = rng.uniform(lo, hi, size=(len(so), 3)).astype(np.float32)
     rd = unit(rng.normal(size=ro.shape))
@@ -174,10 +176,13 @@ def main():
     rays_fixture("practice5_2", 8, 2)
     rays_fixture("lights_mix", 1, 3)
     rays_fixture("practice5_dragon_10k", 4, 4)
+    rays_fixture("rabbid", 2, 5)
     render_fixture("practice5_1", 64, 48, 256)
     render_fixture("practice5_2", 64, 48, 1024)
     render_fixture("lights_mix", 48, 32, 1024)
     render_fixture("practice5_dragon_10k", 64, 64, 256)
+    render_fixture("practice5_dragon_10k", 128, 128, 512)
+    render_fixture("rabbid", 88, 88, 256)
 
 
 if __name__ == "__main__":

@@ -9,6 +9,8 @@
   SYNTHESISED here: the 10k dragon is midpoint-subdivided (shared, slightly displaced edge
   midpoints) to 99,998 triangles inside the same Cornell box, and the material lines follow the
   file names.  bench.py says "synthetic" for these.
+* scenes/rabbid.txt is the course scene `sample.txt` of the reference checkout (52 rotated boxes and
+  ellipsoids lit by the background), kept verbatim as input data.
 * a few small scenes of our own that exercise what the course scenes do not (emissive
   ellipsoid + rotated emissive box in the light mix, metallic, dielectric, multi-primitive
   BVH leaves).

@@ -127,6 +127,16 @@ def test_mix_pdf_vs_reference_golden(rtc, gpu_scenes, name):
     assert np.quantile(rel, 0.999) <= 1e-4, np.quantile(rel, 0.999)
 
 
+@pytest.mark.parametrize("name", RAY_SCENES)
+def test_mix_pdf_towards_lights_vs_reference_golden(rtc, gpu_scenes, name):
+    """As above for directions drawn by the reference's own Distribution::Sample (half of them hit a
+    light).  Grazing hits have |cos| ~ 1e-3 in the denominator: 99 % within 1e-4, 99.9 % within 1e-2."""
+    g = golden(name + "_rays")
+    pdf = gpu_scenes(name).mix_distrib.Pdf(g["pdf_x"], g["pdf_n"], g["lpdf_d"])
+    rel = np.abs(pdf - g["lpdf"]) / np.maximum(np.abs(g["lpdf"]), 1e-12)
+    assert np.quantile(rel, 0.99) <= 1e-4 and np.quantile(rel, 0.999) <= 1e-2, (np.quantile(rel, 0.99), np.quantile(rel, 0.999))
+
+
 @pytest.mark.parametrize("name", ["lights_mix", "practice5_dragon_10k"])
 def test_mix_sample_vs_oracle_same_streams(rtc, gpu_scenes, oracle_scenes, name):
     g = golden(name + "_rays")

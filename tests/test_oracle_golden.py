@@ -88,6 +88,14 @@ def test_mix_pdf_bit_exact(oracle_scenes, name):
     assert np.array_equal(bits(pdf), bits(g["pdf"]))
 
 
+@pytest.mark.parametrize("name", RAY_SCENES)
+def test_mix_pdf_towards_lights_bit_exact(oracle_scenes, name):
+    """Directions drawn by the reference's own Distribution::Sample: half of them hit a light, many graze it."""
+    g = golden(name + "_rays")
+    pdf = oracle_scenes(name).mix_pdf(g["pdf_x"], g["pdf_n"], g["lpdf_d"])
+    assert np.array_equal(bits(pdf), bits(g["lpdf"]))
+
+
 def test_primitive_intersect_bit_exact(oracle_scenes):
     g = golden("primitive_intersect")
     n = 0

@@ -51,6 +51,9 @@ def rays_fixture(name, stride, seed):
     # pdf of the mix distribution at the secondary origins
     pn = nrm[hit]
     pdf = s.mix_pdf(so, pn, sd)
+    # ... and for directions drawn by the reference's own Distribution::Sample (half of them aim at a light)
+    ld = s.ref_mix_sample(so, pn, 12345)
+    lpdf = s.mix_pdf(so, pn, ld)
     tm, data = s.prims()
     aabb, links, root = s.nodes()
     np.savez_compressed(
@@ -58,7 +61,7 @@ def rays_fixture(name, stride, seed):
         xy=xy, cam_o=o, cam_d=d, pid=pid, t=t, nrm=nrm, inter=inter,
         sec_o=so, sec_d=sd, sec_pid=spid, sec_t=st, sec_nrm=snrm, sec_inter=sinter,
         rnd_o=ro, rnd_d=rd, rnd_pid=rpid, rnd_t=rt, rnd_nrm=rnrm, rnd_inter=rinter,
-        pdf_x=so, pdf_n=pn, pdf_d=sd, pdf=pdf,
+        pdf_x=so, pdf_n=pn, pdf_d=sd, pdf=pdf, lpdf_d=ld, lpdf=lpdf,
         prim_type_material=tm, prim_data_crc=np.array([np.bitwise_xor.reduce(data.view(np.uint32).ravel())], np.uint32),
         node_links_crc=np.array([np.bitwise_xor.reduce((links.ravel().astype(np.uint64) * np.arange(1, links.size + 1, dtype=np.uint64)) & np.uint64(0xFFFFFFFF))], np.uint64),
         node_aabb_sum=aabb.astype(np.float64).sum(0), nnodes=np.array([s.nnodes]), root=np.array([root]),

@@ -186,6 +186,8 @@ def main():
     render_fixture("practice5_dragon_10k", 64, 64, 256)
     render_fixture("practice5_dragon_10k", 128, 128, 512)
     render_fixture("rabbid", 88, 88, 256)
+    for sfx in ("", "_glass", "_metal"):
+        render_fixture("practice5_dragon_100k" + sfx, 48, 48, 128)
 
 
 if __name__ == "__main__":

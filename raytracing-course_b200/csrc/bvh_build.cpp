@@ -263,8 +263,23 @@ struct IndexBuilder {
             bool used = i < (int)slots.size();
             // unused slot: a far-away point box and the IREF_NONE marker
             Aabb bx = used ? slots[i].box : Aabb{{60000.f, 60000.f, 60000.f}, {60000.f, 60000.f, 60000.f}};
+#if RTC_NODE_CENTRE_HALF
+            // centre rounded to the nearest half, half-extent rounded UP so that [c - h, c + h] covers the box
+            const float mn[3] = {bx.mn.x, bx.mn.y, bx.mn.z}, mx[3] = {bx.mx.x, bx.mx.y, bx.mx.z};
+            for (int a = 0; a < 3; ++a) {
+                uint16_t c16 = half_bits_rn(0.5f * (mn[a] + mx[a]));
+                double c = (double)half_to_float(c16);
+                double need = std::max((double)mx[a] - c, c - (double)mn[a]);
+                float nf = (float)need;
+                if ((double)nf < need) nf = std::nextafter(nf, INFINITY);
+                hv[a][i] = c16;
+                hv[3 + a][i] = half_up(nf);
+                if ((c16 & 0x7C00u) == 0x7C00u || !(need <= 65504.0)) { hv[a][i] = 0; hv[3 + a][i] = 0x7C00u; }  // beyond fp16: always visited
+            }
+#else
             hv[0][i] = half_down(bx.mn.x); hv[1][i] = half_down(bx.mn.y); hv[2][i] = half_down(bx.mn.z);
             hv[3][i] = half_up(bx.mx.x); hv[4][i] = half_up(bx.mx.y); hv[5][i] = half_up(bx.mx.z);
+#endif
             refs[i] = IREF_NONE;
             if (used) refs[i] = (slots[i].ref & IREF_LEAF) ? slots[i].ref : emit(slots[i].ref, depth + 1);
         }

@@ -390,6 +390,14 @@ RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, Leaf
 // re-tested against its EXACT float box before its primitives are (leaf_test).
 // Slab tests in min/max form with the reciprocal direction.  tc = box entry distance, or -inf when
 // the origin is inside (the reference's `interior`).
+// Reciprocal direction for the slab tests, clamped to +-1e30: a zero direction component would give
+// inf and then inf - inf = NaN in c * inv - o * inv, which the 3-input min/max drop, i.e. the axis would
+// not constrain at all and such a ray (about one in 10^7) would walk a whole slab of the tree and hold
+// a persistent k_traverse launch for milliseconds.  With a finite reciprocal the test is simply exact.
+RT_D vec3 ray_inv(vec3 d) {
+    const float big = 1e30f;
+    return mk3(fminf(fmaxf(1.0f / d.x, -big), big), fminf(fmaxf(1.0f / d.y, -big), big), fminf(fmaxf(1.0f / d.z, -big), big));
+}
 struct NodeVisit {
     uint32_t ref[4];
     bool hit[4];
@@ -418,23 +426,45 @@ RT_D float2 unpack_half2(float word) {
     uint32_t u = __float_as_uint(word);
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
+#if RTC_NODE_CENTRE_HALF
+// child box = centre +- half: entry/exit per axis are tc -+ h * |inv| with tc = c * inv - o * inv, three
+// FFMA and no min/max (the kernel is bound by the ALU pipe, which FMNMX shares with the integer
+// bookkeeping).  Against the exact leaf test (slab) the two roundings can move entry/exit by a few ulp of
+// t; fp16 rounding of c and h (outward) is three orders of magnitude larger except for boxes whose faces
+// are exactly representable in fp16, where a ray within ~1e-6 of grazing a face may be decided the other way.
+RT_D void slab_ch(float cx, float cy, float cz, float hx, float hy, float hz, vec3 inv, vec3 oi, uint32_t ref, bool& hit) {
+    float tx = fmaf(cx, inv.x, -oi.x), ty = fmaf(cy, inv.y, -oi.y), tz = fmaf(cz, inv.z, -oi.z);
+    float ax = fabsf(inv.x), ay = fabsf(inv.y), az = fabsf(inv.z);
+    float t1 = fmaxf(fmaxf(fmaf(-hx, ax, tx), fmaf(-hy, ay, ty)), fmaf(-hz, az, tz));
+    float t2 = fminf(fminf(fmaf(hx, ax, tx), fmaf(hy, ay, ty)), fmaf(hz, az, tz));
+    hit = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
+}
+#endif
 RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) {
     const float4* nd = S.inodes + 4 * (size_t)node;
     float4 q0, q1, q2, q3;
     ldg8(nd, q0, q1);
     ldg8(nd + 2, q2, q3);
     // q0 = min.x[0..3] min.y[0..3] ; q1 = min.z max.x ; q2 = max.y max.z ; q3 = refs
+    // (centre/half layout: centre in place of min, half-extent in place of max)
     const float2 ax01 = unpack_half2(q0.x), ax23 = unpack_half2(q0.y), ay01 = unpack_half2(q0.z), ay23 = unpack_half2(q0.w);
     const float2 az01 = unpack_half2(q1.x), az23 = unpack_half2(q1.y), bx01 = unpack_half2(q1.z), bx23 = unpack_half2(q1.w);
     const float2 by01 = unpack_half2(q2.x), by23 = unpack_half2(q2.y), bz01 = unpack_half2(q2.z), bz23 = unpack_half2(q2.w);
     NodeVisit v;
     v.ref[0] = __float_as_uint(q3.x); v.ref[1] = __float_as_uint(q3.y);
     v.ref[2] = __float_as_uint(q3.z); v.ref[3] = __float_as_uint(q3.w);
+#if RTC_NODE_CENTRE_HALF
+    slab_ch(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, v.ref[0], v.hit[0]);
+    slab_ch(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, v.ref[1], v.hit[1]);
+    slab_ch(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, v.ref[2], v.hit[2]);
+    slab_ch(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, v.ref[3], v.hit[3]);
+#else
     float tc;
     slab(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, v.ref[0], v.hit[0], tc);
     slab(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, v.ref[1], v.hit[1], tc);
     slab(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, v.ref[2], v.hit[2], tc);
     slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, v.ref[3], v.hit[3], tc);
+#endif
     return v;
 }
 // closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)
@@ -484,7 +514,7 @@ RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, vec3 inv, v
 RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int& k, uint32_t* visits, uint32_t* tests) {
     k = 0;
     if (S.iroot == IREF_NONE) return true;
-    vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    vec3 inv = ray_inv(d);
     vec3 oi = o * inv;
     uint32_t stack[kIndexStack];
     int sp = 0;

@@ -30,7 +30,7 @@ RT_D bool pre_step(const DevScene& S, vec3 o, vec3 d, float& cd, uint32_t& id) {
         float te; bool interior; uint32_t l, r;
         return ref_box(S, S.root, o, d, te, interior, l, r);
     }
-    vec3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    vec3 inv = ray_inv(d);
     NodeVisit v = index_visit(S, S.iroot, inv, o * inv);
     return v.hit[0] || v.hit[1] || v.hit[2] || v.hit[3];
 }
@@ -117,7 +117,10 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 #ifndef RTC_VISIT_QUORUM
 #define RTC_VISIT_QUORUM 14   // sweep on B200: 10: 23.6, 12: 22.6, 14: 22.4, 16: 23.0, 20: 23.5 ms/step
 #endif
-constexpr int kVisitQuorum = RTC_VISIT_QUORUM;  // at least this many lanes ready to visit: skip the full vote
+constexpr int kVisitQuorum = RTC_VISIT_QUORUM;
+#ifndef RTC_LAZY_OVERFLOW
+#define RTC_LAZY_OVERFLOW 1
+#endif  // at least this many lanes ready to visit: skip the full vote
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
@@ -138,8 +141,10 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
 
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
-        bool room = sp + nl + 7 <= kStackWords;
+        const bool room = sp + nl + 7 <= kStackWords;
+#if !RTC_LAZY_OVERFLOW
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
+#endif
         const bool canV = active && node != kNone && room;
         const unsigned mV = __ballot_sync(kFullMask, canV);
         const int nV = __popc(mV);
@@ -148,6 +153,11 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
         unsigned mR = 0;
         int nR = 0;
         if (nV < kVisitQuorum) {  // full vote only when visiting would leave too many lanes idle
+#if RTC_LAZY_OVERFLOW
+            // a lane whose stack is full of inner nodes (no noted leaf to free room) gives up and takes the
+            // reference walk in FINISH; checked here only: such a lane is not in mV, so the vote comes
+            if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
+#endif
             canL = active && nl > 0;
             canF = active && node == kNone && nl == 0;
             canR = !active && (pool_left > 0 || !exhausted);
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
                 o = ld3(P.o[ray]);
                 d = ld3(P.d[ray]);
                 cd0 = H.cd[ray];
-                inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                inv = ray_inv(d);
                 oi = o * inv;
                 sp = 0; nl = 0; k = 0; overflow = false;
                 active = true;

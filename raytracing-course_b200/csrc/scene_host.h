@@ -7,7 +7,31 @@
 
 #include "vecmath.h"
 
+// Index-BVH child boxes as fp16 (centre, half-extent) instead of (min, max): the slab test then
+// runs on the FMA pipe (3 FFMA per child and axis) instead of 2 FFMA + 2 FMNMX; k_traverse is bound
+// by the ALU pipe (profiles/r01_experiments.md).  0 selects the min/max layout for A/B runs.
+#ifndef RTC_NODE_CENTRE_HALF
+#define RTC_NODE_CENTRE_HALF 1
+#endif
+
 namespace rtc {
+
+// The course's five homework snapshots of the renderer read five dialects of the scene format and
+// render with five variants of Scene::RayTrace; hw5 is the hot path, hw1-hw4 are its callers' formats
+// (DESIGN.md section 8, row f).  /root/reference/hwN/src/scene.cpp for each.
+enum Dialect : int {
+    DIALECT_HW1 = 1,  // ray casting: colour of the closest primitive, no tone mapping
+    DIALECT_HW2 = 2,  // Whitted: ambient + point/directional lights with shadows, metallic, dielectric (Schlick blend)
+    DIALECT_HW3 = 3,  // path tracing, uniform-hemisphere sampling (2 C L cos), EMISSION / SAMPLES
+    DIALECT_HW4 = 4,  // path tracing with the cosine + light mix distribution (hw5 without triangles and BVH)
+    DIALECT_HW5 = 5   // + TRIANGLE, SAH BVH
+};
+
+// hw2 light (src/lights.cpp): directional (dir) or point (pos, attenuation c0 + c1 d + c2 d^2)
+struct PointLight {
+    vec3 intensity{0, 0, 0}, pos{0, 0, 0}, att{0, 0, 0}, dir{0, 0, 0};
+    int directed = 0;
+};
 
 // PRIMITIVE_TYPE / MATERIAL values follow include/primitives.h:13-18 and include/materials.h
 enum PrimType : int { PT_PLANE = 1, PT_BOX = 2, PT_ELLIPSOID = 4, PT_TRIANGLE = 8 };
@@ -73,12 +97,16 @@ struct FlatScene {
     std::vector<f4> ubox;              // 2 x f4 per primitive slot: (min,0) (max,0) of the reference leaf starting there
     std::vector<f4> planes;            // 2 x f4 per plane: (n, bits(prim id)) (pos, bits(no rotation))
     std::vector<int32_t> lights;
+    std::vector<f4> plights;           // hw2: 4 x f4 per light: (intensity, bits(directed)) (pos,0) (attenuation,0) (normalised dir,0)
     uint32_t index_depth = 0, ref_depth = 0, units = 0;
 };
 
 struct HostScene {
+    int dialect = DIALECT_HW5;
     Camera cam;
     vec3 background{0, 0, 0};
+    vec3 ambient{0, 0, 0};                 // hw2 AMBIENT_LIGHT
+    std::vector<PointLight> point_lights;  // hw2 NEW_LIGHT blocks
     unsigned ray_depth = 0, samples = 0;
     std::vector<Primitive> prims;  // final order after init()
     uint32_t nbvh = 0;             // non-plane primitives, stored first
@@ -87,7 +115,8 @@ struct HostScene {
     std::vector<int32_t> lights;   // emissive boxes / ellipsoids
     FlatScene flat;
 
-    // Scene::Load (src/sceneload.cpp:112-176)
+    // Scene::Load (hw5 src/sceneload.cpp:112-176; hwN src/scene.cpp Scene::Load for the other dialects):
+    // only the words of `dialect` are commands, the rest is reported as unexpected and skipped
     void parse(const std::string& text);
     // Scene::InitScene (src/scene.cpp:7-40) + our index structures + flattening
     void init();

@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--ref-height", type=int, default=64)
     ap.add_argument("--ref-spp", type=int, default=8)
     ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--no-pipeline", action="store_true", help="render the timed frames strictly one after the other")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +198,12 @@ def main():
     # spp sharding: rank r renders samples [lo, hi)
     lo, hi = rtc.shard_samples(spp, rank, world)
     npix = W * H
-    accum = torch.zeros(npix * 3, dtype=torch.float32, device=dev)
+    # Frames are pipelined two deep: frame i+1 starts on the other stream (own accumulation buffer) while the
+    # last kernels of frame i drain, so the tail of a persistent k_traverse launch -- a few long rays on an
+    # otherwise idle GPU -- overlaps the next frame's first kernels instead of ending the step.  Every frame is
+    # still rendered, reduced and complete inside the timed region.
+    accums = [torch.zeros(npix * 3, dtype=torch.float32, device=dev) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     rgb = torch.zeros(npix * 3, dtype=torch.uint8, device=dev)
     host_rgb = torch.zeros(npix * 3, dtype=torch.uint8).pin_memory()
 
@@ -206,26 +212,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def render_step(step, e2e):
+    def render_step(step, e2e, pipelined=False):
         h2d = 0
-        if e2e:
-            h2d = scene.upload()                      # host scene arrays -> HBM
-        accum.zero_()
-        scene.render_accumulate(accum.data_ptr(), seed=1000 + step, sample_begin=lo, sample_count=hi - lo)
-        if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-        if e2e and rank == 0:
-            scene.render_resolve(accum.data_ptr(), spp, rgb.data_ptr())
-            host_rgb.copy_(rgb, non_blocking=False)   # D2H of the 8-bit frame
-        return h2d
+        if not pipelined:
+            accum = accums[0]
+            if e2e:
+                h2d = scene.upload()                      # host scene arrays -> HBM
+            accum.zero_()
+            scene.render_accumulate(accum.data_ptr(), seed=1000 + step, sample_begin=lo, sample_count=hi - lo)
+            if world > 1:
+                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            if e2e and rank == 0:
+                scene.render_resolve(accum.data_ptr(), spp, rgb.data_ptr())
+                host_rgb.copy_(rgb, non_blocking=False)   # D2H of the 8-bit frame
+            return h2d
+        slot = step & 1
+        accum, st = accums[slot], streams[slot]
+        with torch.cuda.stream(st):
+            accum.zero_()
+            scene.render_accumulate(accum.data_ptr(), seed=1000 + step, sample_begin=lo, sample_count=hi - lo,
+                                    stream=st.cuda_stream)
+            if world > 1:
+                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+        return 0
 
-    def timed(nsteps, e2e, first_step):
+    def timed(nsteps, e2e, first_step, pipelined=False):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
         a.record()
+        for st in streams:
+            st.wait_stream(cur)
         h2d = 0
         for i in range(nsteps):
-            h2d = render_step(first_step + i, e2e)
+            h2d = render_step(first_step + i, e2e, pipelined)
+        for st in streams:
+            cur.wait_stream(st)
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
@@ -235,7 +257,7 @@ def main():
 
     # ---- warm-up (also sizes the wavefront buffers), then an untimed instrumented pass
     for i in range(max(args.warmup, 3)):
-        render_step(i, False)
+        render_step(i, False, not args.no_pipeline)
     barrier()
     scene.reset_counters()
     scene.set_profiling(kernel_events=False, count_visits=True)
@@ -247,7 +269,7 @@ def main():
     scene.reset_counters()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_total, _ = timed(args.steps, False, 100)
+    ms_total, _ = timed(args.steps, False, 100, pipelined=not args.no_pipeline)
     clocks = sampler.result()
     cnt = scene.counters()
     # ---- the same steps again with CUDA events around every kernel (roofline durations)
@@ -320,7 +342,8 @@ def main():
                 "config": {"workload": args.scene, "width": W, "height": H, "spp": spp, "ray_depth": depth,
                            "paths_per_step": npix * spp, "triangles": scene.nbvh, "parallelism": "spp-shard x%d" % world,
                            "l2": "wavefront state (%.0f MB/step) exceeds the 126 MB L2" % (min(npix * (hi - lo), 1 << 23) * 148 / 1e6),
-                           "traversal": "index" if args.traversal == 0 else "reftree"},
+                           "traversal": "index" if args.traversal == 0 else "reftree",
+                           "frames_in_flight": 1 if args.no_pipeline else 2},
                 "mrays_per_s": mrays, "rays_per_path": total_rays / max(total_paths, 1),
                 "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": int(npix * 3), "ms_per_step": e2e_ms / args.steps},

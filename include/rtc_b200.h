@@ -45,6 +45,19 @@ int rtc_device_count(void);
 rtc_scene* rtc_scene_load(const char* path, int device);
 rtc_scene* rtc_scene_parse(const char* text, long len, int device);
 void rtc_scene_free(rtc_scene* s);
+/* ---- the earlier snapshots of the same renderer (hw1..hw4 src/scene.cpp Scene::Load / Scene::Render, each
+ *      behind its own `run.sh <scene> <out.ppm>`): `dialect` 1..5 selects the vocabulary of the scene
+ *      reader and the variant of Scene::RayTrace (1 ray casting, 2 Whitted with point / directional lights,
+ *      3 path tracing with uniform-hemisphere sampling, 4 cosine + light mix without triangles, 5 = the two
+ *      calls above).  hw1 and hw2 have no samples: the render calls produce the one deterministic frame. */
+#define RTC_DIALECT_HW1 1
+#define RTC_DIALECT_HW2 2
+#define RTC_DIALECT_HW3 3
+#define RTC_DIALECT_HW4 4
+#define RTC_DIALECT_HW5 5
+rtc_scene* rtc_scene_load_dialect(const char* path, int device, int dialect);
+rtc_scene* rtc_scene_parse_dialect(const char* text, long len, int device, int dialect);
+int rtc_scene_dialect(const rtc_scene* s);
 /* re-upload the already built host scene to its device (bench e2e: the per-step H2D copy).
  * returns the number of bytes copied through *h2d_bytes. */
 int rtc_scene_upload(rtc_scene* s, uint64_t* h2d_bytes);

@@ -65,7 +65,13 @@ typedef struct { float t; v3 n; int interior; } isec_t;
 typedef struct { isec_t isec; int id; } rayisec_t;
 typedef struct { v3 o, d; } ray_t;
 
+/* hw2 light (hw2 src/lights.cpp) */
+typedef struct { v3 intensity, pos, att, dir; int directed; } plight_t;
+
 struct orc_scene {
+    int dialect;                 /* 1..5: which homework snapshot's Scene::Load / Scene::RayTrace apply */
+    v3 ambient;                  /* hw2 AMBIENT_LIGHT */
+    plight_t* plights; int nplights, plcap;
     unsigned width, height, ray_depth, samples;
     v3 bg, cam_pos, cam_right, cam_up, cam_forward;
     float fov_x;
@@ -76,19 +82,20 @@ struct orc_scene {
 };
 
 static const float INF_ = 1e18f;      /* bvh.h:9 */
-static const float SCENE_EPS = 1e-4f; /* scene.h:64 */
 
 /* ------------------------------------------------------------------ primitive intersections */
 /* primitives.cpp:55-66 */
-static int isect_plane(ray_t r, v3 n, isec_t* out) {
+/* IntersectPlane drops t > 1e5 from hw4 on (hw4 src/primitives.cpp:47, hw5 :58); hw1..hw3 have no limit */
+static int isect_plane_tmax(ray_t r, v3 n, float tmax, isec_t* out) {
     float t = -vdot(r.o, n) / vdot(r.d, n);
-    if (t > 1e5) return 0;
+    if (t > tmax) return 0;
     if (t > 0) {
         if (vdot(r.d, n) >= 0) { out->t = t; out->n = vscale(-1.0f, n); out->interior = 1; return 1; }
         out->t = t; out->n = n; out->interior = 0; return 1;
     }
     return 0;
 }
+static int isect_plane(ray_t r, v3 n, isec_t* out) { return isect_plane_tmax(r, n, 1e5f, out); }
 /* primitives.cpp:70-117 */
 static int isect_box(ray_t r, v3 s, isec_t* out) {
     v3 t1v = vdiv(vsub(vscale(-1.f, s), r.o), r.d);
@@ -148,7 +155,7 @@ static int isect_triangle(ray_t r, v3 a, v3 b, v3 c, isec_t* out) {
     return 1;
 }
 /* primitives.cpp:14-52 */
-static int prim_intersect(const prim_t* pr, ray_t ray, isec_t* out) {
+static int prim_intersect_ex(const prim_t* pr, ray_t ray, float plane_tmax, isec_t* out) {
     quat qc = qconj(pr->rot);
     ray_t rr;
     rr.o = qrot(qc, vadd(ray.o, vscale(-1.0f, pr->pos)));
@@ -156,7 +163,7 @@ static int prim_intersect(const prim_t* pr, ray_t ray, isec_t* out) {
     isec_t is;
     int ok = 0;
     switch (pr->type) {
-        case PT_PLANE: ok = isect_plane(rr, pr->d0, &is); break;
+        case PT_PLANE: ok = isect_plane_tmax(rr, pr->d0, plane_tmax, &is); break;
         case PT_BOX: ok = isect_box(rr, pr->d0, &is); break;
         case PT_ELLIPSOID: ok = isect_ellipsoid(rr, pr->d0, &is); break;
         case PT_TRIANGLE: ok = isect_triangle(rr, pr->d0, pr->d1, pr->d2, &is); break;
@@ -168,6 +175,7 @@ static int prim_intersect(const prim_t* pr, ray_t ray, isec_t* out) {
     out->interior = is.interior;
     return 1;
 }
+static int prim_intersect(const prim_t* pr, ray_t ray, isec_t* out) { return prim_intersect_ex(pr, ray, 1e5f, out); }
 
 /* ------------------------------------------------------------------ AABB / BVH (bvh.cpp) */
 static aabb_t aabb_empty(void) { aabb_t b = {{INF_, INF_, INF_}, {-INF_, -INF_, -INF_}}; return b; }
@@ -421,7 +429,22 @@ static rayisec_t bvh_intersect(const orc_scene* s, ray_t ray, float closest, uin
     return best;
 }
 /* scene.cpp:46-77 */
+/* hw2/hw3 src/scene.cpp:189-211 (closest_dist = -1, `isec.t <= tmax`), hw4 src/scene.cpp:209-227
+   (closest_dist = 2e9): every primitive, in file order; the first of equal distances wins */
+static rayisec_t ray_intersection_linear(const orc_scene* s, ray_t ray, float tmax) {
+    rayisec_t ret; memset(&ret, 0, sizeof ret); ret.id = -1;
+    const float plane_tmax = s->dialect <= 3 ? 3.0e38f : 1e5f;
+    float closest = s->dialect == 4 ? 2e9f : -1.f;
+    for (int i = 0; i < s->nprims; ++i) {
+        isec_t is;
+        if (!prim_intersect_ex(&s->prims[i], ray, plane_tmax, &is)) continue;
+        if (s->dialect == 4) { if (is.t < closest) { closest = is.t; ret.isec = is; ret.id = i; } }
+        else if (is.t <= tmax && (closest == -1.f || is.t < closest)) { closest = is.t; ret.isec = is; ret.id = i; }
+    }
+    return ret;
+}
 static rayisec_t ray_intersection(const orc_scene* s, ray_t ray) {
+    if (s->dialect != 5) return ray_intersection_linear(s, ray, 1e18f);
     rayisec_t ret; memset(&ret, 0, sizeof ret); ret.id = -1;
     float closest = INF_;
     for (int i = 0; i < s->nprims; ++i) {
@@ -439,12 +462,18 @@ static rayisec_t ray_intersection(const orc_scene* s, ray_t ray) {
 /* ------------------------------------------------------------------ scene loading (sceneload.cpp) */
 enum { C_EMPTY, C_DIM, C_BG, C_CPOS, C_CRIGHT, C_CUP, C_CFWD, C_FOV, C_NEWPRIM, C_PLANE, C_ELLIPSOID, C_BOX,
        C_POSITION, C_ROTATION, C_COLOR, C_RAYDEPTH, C_METALLIC, C_DIELECTRIC, C_IOR, C_SAMPLES, C_EMISSION,
-       C_TRIANGLE, C_UNKNOWN };
-static int get_command(const char* w) { /* sceneload.cpp:8-33 */
+       C_TRIANGLE, C_AMBIENT, C_NEWLIGHT, C_LINTENS, C_LDIR, C_LPOS, C_LATT, C_UNKNOWN };
+/* get_command of each snapshot (hw5 sceneload.cpp:8-33; hw1..hw4 src/scene.cpp:8-36): a word outside the
+   snapshot's vocabulary is unknown there */
+static int get_command(const char* w, int dialect) {
     static const char* names[] = {"", "DIMENSIONS", "BG_COLOR", "CAMERA_POSITION", "CAMERA_RIGHT", "CAMERA_UP",
         "CAMERA_FORWARD", "CAMERA_FOV_X", "NEW_PRIMITIVE", "PLANE", "ELLIPSOID", "BOX", "POSITION", "ROTATION",
-        "COLOR", "RAY_DEPTH", "METALLIC", "DIELECTRIC", "IOR", "SAMPLES", "EMISSION", "TRIANGLE"};
-    for (int i = 0; i < 22; ++i) if (strcmp(w, names[i]) == 0) return i;
+        "COLOR", "RAY_DEPTH", "METALLIC", "DIELECTRIC", "IOR", "SAMPLES", "EMISSION", "TRIANGLE",
+        "AMBIENT_LIGHT", "NEW_LIGHT", "LIGHT_INTENSITY", "LIGHT_DIRECTION", "LIGHT_POSITION", "LIGHT_ATTENUATION"};
+    static const int first[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 5, 2, 2, 2, 2, 2, 2};
+    static const int last[]  = {5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 2, 2, 2, 2, 2, 2};
+    for (int i = 0; i < 28; ++i)
+        if (strcmp(w, names[i]) == 0) return (first[i] <= dialect && dialect <= last[i]) ? i : C_UNKNOWN;
     return C_UNKNOWN;
 }
 typedef struct { const char* p; const char* end; } cursor;
@@ -491,7 +520,7 @@ static void prim_reset(prim_t* p, int type) {
     p->type = type; p->rot.w = 1.f; p->material = MAT_DIFFUSE; /* primitives.h:43-47 defaults */
 }
 /* sceneload.cpp:35-110 ; returns 1 and fills rest[] when an unknown command ended the block */
-static int load_primitive(cursor* c, prim_t* pr, char* rest, size_t restcap) {
+static int load_primitive(cursor* c, int dialect, prim_t* pr, char* rest, size_t restcap) {
     char line[4096], word[64];
     prim_reset(pr, 0);
     rest[0] = 0;
@@ -499,7 +528,7 @@ static int load_primitive(cursor* c, prim_t* pr, char* rest, size_t restcap) {
         toks t = {line, 0};
         tok_word(&t, word, sizeof word);
         t.fail = 0;
-        int cmd = get_command(word);
+        int cmd = get_command(word, dialect);
         if (cmd == C_EMPTY) break;
         switch (cmd) {
             case C_ELLIPSOID: { v3 r = {0, 0, 0}; tok_v3(&t, &r); prim_reset(pr, PT_ELLIPSOID); pr->d0 = r; break; }
@@ -526,10 +555,34 @@ static void add_prim(orc_scene* s, const prim_t* p) {
     if (s->nprims == s->cap) { s->cap = s->cap ? s->cap * 2 : 1024; s->prims = (prim_t*)realloc(s->prims, sizeof(prim_t) * (size_t)s->cap); }
     s->prims[s->nprims] = *p; s->prims[s->nprims].orig = s->nprims; s->nprims++;
 }
+/* hw2 LoadLight, hw2 src/scene.cpp:120-168 */
+static int load_light(cursor* c, plight_t* l, char* rest, size_t restcap) {
+    char line[4096], word[64];
+    memset(l, 0, sizeof *l);
+    rest[0] = 0;
+    while (next_line(c, line, sizeof line)) {
+        toks t = {line, 0};
+        tok_word(&t, word, sizeof word);
+        t.fail = 0;
+        int cmd = get_command(word, 2);
+        if (cmd == C_EMPTY) break;
+        switch (cmd) {
+            case C_LINTENS: tok_v3(&t, &l->intensity); break;
+            case C_LPOS: tok_v3(&t, &l->pos); break;
+            case C_LDIR: tok_v3(&t, &l->dir); l->directed = 1; break;
+            case C_LATT: tok_v3(&t, &l->att); break;
+            default: snprintf(rest, restcap, "%s", word); return 1;
+        }
+    }
+    return 0;
+}
 static void init_scene(orc_scene* s);
+static void init_scene_linear(orc_scene* s);
 
-orc_scene* orc_scene_parse(const char* text, long len) { /* sceneload.cpp:112-176 */
+orc_scene* orc_scene_parse(const char* text, long len) { return orc_scene_parse_dialect(text, len, 5); }
+orc_scene* orc_scene_parse_dialect(const char* text, long len, int dialect) { /* sceneload.cpp:112-176; hwN src/scene.cpp Scene::Load */
     orc_scene* s = (orc_scene*)calloc(1, sizeof *s);
+    s->dialect = dialect;
     cursor c = {text, text + len};
     char line[4096], word[64], rest[64];
     while (next_line(&c, line, sizeof line)) {
@@ -537,7 +590,7 @@ orc_scene* orc_scene_parse(const char* text, long len) { /* sceneload.cpp:112-17
         tok_word(&t, word, sizeof word);
         t.fail = 0;
         for (;;) { /* "pasrse_command_again" */
-            int cmd = get_command(word);
+            int cmd = get_command(word, dialect);
             int again = 0;
             switch (cmd) {
                 case C_EMPTY: break;
@@ -550,10 +603,20 @@ orc_scene* orc_scene_parse(const char* text, long len) { /* sceneload.cpp:112-17
                 case C_FOV: tok_float(&t, &s->fov_x); break;
                 case C_RAYDEPTH: tok_uint(&t, &s->ray_depth); break;
                 case C_SAMPLES: tok_uint(&t, &s->samples); break;
+                case C_AMBIENT: tok_v3(&t, &s->ambient); break;
+                case C_NEWLIGHT:
                 case C_NEWPRIM: {
                     prim_t p;
-                    int has_rest = load_primitive(&c, &p, rest, sizeof rest);
-                    add_prim(s, &p);
+                    int has_rest;
+                    if (cmd == C_NEWLIGHT) {
+                        plight_t l;
+                        has_rest = load_light(&c, &l, rest, sizeof rest);
+                        if (s->nplights == s->plcap) { s->plcap = s->plcap ? s->plcap * 2 : 8; s->plights = (plight_t*)realloc(s->plights, sizeof(plight_t) * (size_t)s->plcap); }
+                        s->plights[s->nplights++] = l;
+                    } else {
+                        has_rest = load_primitive(&c, dialect, &p, rest, sizeof rest);
+                        add_prim(s, &p);
+                    }
                     if (has_rest && rest[0]) {
                         /* the reference re-dispatches the leftover command name but keeps the
                            (exhausted) stream of the NEW_PRIMITIVE line: its arguments are lost */
@@ -569,21 +632,38 @@ orc_scene* orc_scene_parse(const char* text, long len) { /* sceneload.cpp:112-17
             if (!again) break;
         }
     }
-    init_scene(s);
+    if (dialect == 5) init_scene(s);
+    else init_scene_linear(s);
     return s;
 }
-orc_scene* orc_scene_load(const char* path) {
+orc_scene* orc_scene_load(const char* path) { return orc_scene_load_dialect(path, 5); }
+orc_scene* orc_scene_load_dialect(const char* path, int dialect) {
     FILE* f = fopen(path, "rb");
     if (!f) return NULL;
     fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
     char* buf = (char*)malloc((size_t)n + 1);
     if (fread(buf, 1, (size_t)n, f) != (size_t)n) { fclose(f); free(buf); return NULL; }
     fclose(f); buf[n] = 0;
-    orc_scene* s = orc_scene_parse(buf, n);
+    orc_scene* s = orc_scene_parse_dialect(buf, n, dialect);
     free(buf);
     return s;
 }
-void orc_scene_free(orc_scene* s) { if (!s) return; free(s->prims); free(s->nodes); free(s->lights); free(s); }
+void orc_scene_free(orc_scene* s) { if (!s) return; free(s->prims); free(s->nodes); free(s->lights); free(s->plights); free(s); }
+
+/* hw1..hw4 keep the primitives in file order and have no BVH (Scene::RayIntersection loops over all of
+   them); hw4's InitDistribution is the same list of emissive boxes / ellipsoids (hw4 src/scene.cpp Scene::Load tail) */
+static void init_scene_linear(orc_scene* s) {
+    int n = s->nprims;
+    s->nbvh = 0;
+    s->lights = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    s->nlights = 0;
+    if (s->dialect != 4) return;
+    for (int i = 0; i < n; ++i) {
+        const prim_t* p = &s->prims[i];
+        if (!(p->emission.x > 0 || p->emission.y > 0 || p->emission.z > 0)) continue;
+        if (p->type == PT_BOX || p->type == PT_ELLIPSOID) s->lights[s->nlights++] = i;
+    }
+}
 
 /* scene.cpp:7-40 : InitBVH (partition non-planes first, build) + InitDistribution */
 static void init_scene(orc_scene* s) {
@@ -798,6 +878,7 @@ static v3 reflect_dir(v3 normal, v3 dir) { /* scene.cpp:79-81 */
 /* scene.cpp:83-178 unrolled into a loop: L = sum_k beta_k * E_k, beta_k = prod of bounce weights */
 static v3 ray_trace(const orc_scene* s, uint32_t seed, uint32_t pixel, uint32_t sample, ray_t ray, uint64_t* nrays) {
     v3 L = V(0, 0, 0), beta = V(1, 1, 1);
+    const float SCENE_EPS = s->dialect <= 3 ? 1e-3f : 1e-4f; /* hw2/hw3 include/scene.h:60, hw4/hw5 include/scene.h:57/64 */
     for (unsigned bounce = 1; bounce <= s->ray_depth; ++bounce) {
         rayisec_t h = ray_intersection(s, ray);
         (*nrays)++;
@@ -807,7 +888,16 @@ static v3 ray_trace(const orc_scene* s, uint32_t seed, uint32_t pixel, uint32_t 
         v3 p = vadd(ray.o, vscale(t, ray.d));
         L = vadd(L, vmul(beta, pr->emission));
         rng_t g = {seed, pixel, sample, bounce};
-        if (pr->material == MAT_DIFFUSE) {
+        if (pr->material == MAT_DIFFUSE && s->dialect == 3) {
+            /* hw3 src/scene.cpp:238-249: a direction uniform on the sphere, mirrored into the hemisphere of
+               the normal; L = E + C * 2 * dot(w, n) * L_in(w) */
+            uint32_t b1[4]; rng_block(&g, 1, b1);
+            v3 dir = normal_vec(b1);
+            float cs = vdot(dir, normal);
+            if (cs < 0) { dir = vscale(-1.f, dir); cs = -cs; }
+            beta = vmul(beta, V(pr->col.x * (2 * cs), pr->col.y * (2 * cs), pr->col.z * (2 * cs)));
+            ray.o = vadd(p, vscale(SCENE_EPS, dir)); ray.d = dir;
+        } else if (pr->material == MAT_DIFFUSE) {
             v3 p_outer = vadd(p, vscale(SCENE_EPS, normal));
             v3 dir = mix_sample(s, &g, p_outer, normal);
             float cs = vdot(dir, normal);
@@ -852,9 +942,141 @@ static v3 ray_trace(const orc_scene* s, uint32_t seed, uint32_t pixel, uint32_t 
     return L;
 }
 
+/* ---- hw2: Scene::RayTrace, hw2 src/scene.cpp:262-341 (recursive, both dielectric branches followed) */
+static void calc_light(const plight_t* l, v3 p, v3* colour, v3* dir, float* dist) { /* hw2 src/lights.cpp:7-23 */
+    if (l->directed) { *colour = l->intensity; *dir = vnormalize(l->dir); *dist = 1e18f; return; }
+    v3 to = vsub(l->pos, p);
+    float d = vlength(to);
+    float k = (float)(1. / (double)(l->att.x + l->att.y * d + l->att.z * d * d));
+    *colour = vscale(k, l->intensity); *dir = vnormalize(to); *dist = d;
+}
+static v3 whitted(const orc_scene* s, ray_t ray, unsigned depth, uint64_t* nrays) {
+    const float eps = 1e-3f; /* hw2 include/scene.h:60 */
+    if (depth == 0) return V(0, 0, 0);
+    rayisec_t h = ray_intersection_linear(s, ray, 1e18f);
+    (*nrays)++;
+    if (h.id == -1) return s->bg;
+    const prim_t* pr = &s->prims[h.id];
+    v3 normal = h.isec.n; int interior = h.isec.interior;
+    v3 p = vadd(ray.o, vscale(h.isec.t, ray.d));
+    v3 rd = reflect_dir(normal, vnormalize(ray.d));
+    if (pr->material == MAT_DIFFUSE) {
+        v3 sum = s->ambient;
+        for (int l = 0; l < s->nplights; ++l) {
+            v3 colour, dir; float dist;
+            calc_light(&s->plights[l], p, &colour, &dir, &dist);
+            float k = vdot(dir, normal);
+            if (k >= 0) {
+                ray_t sh = {vadd(p, vscale(eps, dir)), dir};
+                (*nrays)++;
+                if (ray_intersection_linear(s, sh, dist).id == -1) sum = vadd(sum, vscale(k, colour));
+            }
+        }
+        return vmul(sum, pr->col);
+    }
+    ray_t rr = {vadd(p, vscale(eps, rd)), rd};
+    if (pr->material == MAT_METALLIC) return vmul(pr->col, whitted(s, rr, depth - 1, nrays));
+    v3 reflected = whitted(s, rr, depth - 1, nrays);
+    float eta1 = 1.f, eta2 = pr->ior;
+    if (interior) { float tmp = eta1; eta1 = eta2; eta2 = tmp; }
+    v3 dir = vscale(-1.f, vnormalize(ray.d));
+    float dn = vdot(normal, dir);
+    float sin2 = (float)((double)(eta1 / eta2) * sqrt((double)(1 - dn * dn)));
+    if (fabsf(sin2) > 1.) return reflected;
+    float cos2 = (float)sqrt((double)(1 - sin2 * sin2));
+    float e = eta1 / eta2;
+    v3 fr = vadd(vscale(e, vscale(-1.f, dir)), vscale(e * dn - cos2, normal));
+    ray_t fray = {vadd(p, vscale(eps, fr)), fr};
+    v3 refr = whitted(s, fray, depth - 1, nrays);
+    if (!interior) refr = vmul(refr, pr->col);
+    float r0 = (float)pow((double)((eta1 - eta2) / (eta1 + eta2)), 2.);
+    float r = (float)((double)r0 + (double)(1 - r0) * pow((double)(1 - dn), 5.));
+    return vadd(vscale(r, reflected), vscale(1 - r, refr));
+}
+/* pixel-centre camera ray, hw2 src/scene.cpp:229-237: nx, ny evaluated in double with (x + 0.5) */
+static ray_t cam_ray_centre(const orc_scene* s, unsigned x, unsigned y) {
+    float tan_fov_x = (float)tan((double)(s->fov_x / 2));
+    float tan_fov_y = tan_fov_x * (float)s->height / (float)s->width;
+    float nx = (float)((2 * (x + 0.5) / s->width - 1) * (double)tan_fov_x);
+    float ny = (float)(-1.f * (2 * (y + 0.5) / s->height - 1) * (double)tan_fov_y);
+    ray_t r;
+    r.o = s->cam_pos;
+    r.d = vadd(vadd(vscale(nx, s->cam_right), vscale(ny, s->cam_up)), vscale(1.f, s->cam_forward));
+    return r;
+}
+/* ---- hw1: Scene::raytrace, hw1 src/scene.cpp:40-56, everything in double (hw1 include/point.h) */
+typedef struct { double x, y, z; } d3;
+static d3 D3(v3 a) { d3 r = {a.x, a.y, a.z}; return r; }
+static d3 dsub(d3 a, d3 b) { d3 r = {a.x - b.x, a.y - b.y, a.z - b.z}; return r; }
+static double ddot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static d3 dcross_hw1(d3 a, d3 p) { d3 r = {a.z * p.y - a.y * p.z, a.x * p.z - a.z * p.x, a.y * p.x - a.x * p.y}; return r; } /* point.cpp:21-23 */
+typedef struct { d3 v; double w; } dq;
+static dq dqmul(dq a, dq q) { /* quaternion.cpp:11-13 */
+    d3 c = dcross_hw1(a.v, q.v);
+    dq r = {{a.w * q.v.x + q.w * a.v.x + c.x, a.w * q.v.y + q.w * a.v.y + c.y, a.w * q.v.z + q.w * a.v.z + c.z}, a.w * q.w - ddot(a.v, q.v)};
+    return r;
+}
+static d3 dqtransform(dq q, d3 x) { /* quaternion.cpp:19-21 */
+    dq px = {x, 0.}, cj = {{-q.v.x, -q.v.y, -q.v.z}, q.w};
+    return dqmul(dqmul(q, px), cj).v;
+}
+static int hw1_intersect(const prim_t* pr, d3 o, d3 d, double* t_out) { /* hw1 src/primitives.cpp:4-103 */
+    dq q = {{pr->rot.x, pr->rot.y, pr->rot.z}, pr->rot.w};
+    o = dqtransform(q, dsub(o, D3(pr->pos)));
+    d = dqtransform(q, d);
+    d3 g = D3(pr->d0);
+    if (pr->type == PT_PLANE) {
+        double t = -ddot(o, g) / ddot(d, g);
+        if (t < 0) return 0;
+        *t_out = t; return 1;
+    }
+    if (pr->type == PT_BOX) {
+        double ax = (-g.x - o.x) / d.x, bx = (g.x - o.x) / d.x, ay = (-g.y - o.y) / d.y, by = (g.y - o.y) / d.y;
+        double az = (-g.z - o.z) / d.z, bz = (g.z - o.z) / d.z;
+        double t1 = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmin(az, bz));
+        double t2 = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmax(az, bz));
+        if (t1 > t2 || t2 < 0) return 0;
+        *t_out = t1 < 0 ? t2 : t1; return 1;
+    }
+    d3 dr = {d.x / g.x, d.y / g.y, d.z / g.z}, orr = {o.x / g.x, o.y / g.y, o.z / g.z};
+    double a = ddot(dr, dr), b = 2 * ddot(orr, dr), c = ddot(orr, orr) - 1;
+    double disc = b * b - 4 * a * c;
+    if (disc <= 0) return 0;
+    double x1 = (-b - sqrt(disc)) / (2 * a), x2 = (-b + sqrt(disc)) / (2 * a);
+    if (x1 > x2) { double tmp = x1; x1 = x2; x2 = tmp; }
+    if (x2 < 0) return 0;
+    *t_out = x1 < 0 ? x2 : x1; return 1;
+}
+static v3 raycast_hw1(const orc_scene* s, unsigned x, unsigned y) {
+    double tan_fov_x = tan((double)s->fov_x / 2), tan_fov_y = tan_fov_x * s->height / s->width;
+    float nx = (float)((2 * (x + 0.5) / s->width - 1) * tan_fov_x);
+    float ny = (float)(-1.f * (2 * (y + 0.5) / s->height - 1) * tan_fov_y);
+    d3 r = D3(s->cam_right), u = D3(s->cam_up), f = D3(s->cam_forward);
+    d3 d = {nx * r.x + ny * u.x + 1.f * f.x, nx * r.y + ny * u.y + 1.f * f.y, nx * r.z + ny * u.z + 1.f * f.z};
+    v3 ans = s->bg;
+    double closest = -1;
+    for (int i = 0; i < s->nprims; ++i) {
+        double t;
+        if (hw1_intersect(&s->prims[i], D3(s->cam_pos), d, &t) && (closest == -1 || t < closest)) { closest = t; ans = s->prims[i].col; }
+    }
+    return ans;
+}
+
 void orc_render_sum(const orc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t sample_count,
                     long pix_begin, long pix_end, float* out_sum, uint64_t counters[2], int nthreads) {
     uint64_t paths = 0, rays = 0;
+    if (s->dialect <= 2) { /* deterministic snapshots: the frame itself, once, whatever the sample range */
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : paths, rays)
+        for (long i = pix_begin; i < pix_end; ++i) {
+            unsigned x = (unsigned)(i % s->width), y = (unsigned)(i / s->width);
+            uint64_t nr = 0;
+            v3 c = s->dialect == 1 ? raycast_hw1(s, x, y) : whitted(s, cam_ray_centre(s, x, y), s->ray_depth, &nr);
+            out_sum[3 * (i - pix_begin) + 0] = c.x; out_sum[3 * (i - pix_begin) + 1] = c.y; out_sum[3 * (i - pix_begin) + 2] = c.z;
+            paths++; rays += nr;
+        }
+        if (counters) { counters[0] += paths; counters[1] += rays; }
+        return;
+    }
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #else
@@ -869,6 +1091,9 @@ void orc_render_sum(const orc_scene* s, uint32_t seed, uint32_t sample_begin, ui
             rng_t g = {seed, (uint32_t)i, smp, 0};
             uint32_t b[4]; rng_block(&g, 0, b);
             float fx = (float)x + u01(b[0]), fy = (float)y + u01(b[1]); /* scene.cpp:197-198 */
+            /* hw3's Camera::GetToRay(float, float) still adds the half pixel of its integer ancestor
+               (hw3 src/scene.cpp:186-187): the jittered samples cover [x + 0.5, x + 1.5) */
+            if (s->dialect == 3) { fx = (float)((double)fx + 0.5); fy = (float)((double)fy + 0.5); }
             uint64_t nr = 0;
             v3 c = ray_trace(s, seed, (uint32_t)i, smp, cam_ray(s, fx, fy), &nr);
             sum = vadd(sum, c);
@@ -893,6 +1118,12 @@ void orc_tonemap_u8(long npix, const float* rgb, uint8_t* out) {
         out[i] = (unsigned char)round((double)(255 * g)); /* color.cpp:43-49 */
     }
 }
+
+/* hw1 Color::toUInts without tone mapping, hw1 src/color.cpp:10-16 */
+void orc_flat_u8(long npix, const float* rgb, uint8_t* out) {
+    for (long i = 0; i < 3 * npix; ++i) out[i] = (unsigned char)round(255 * (double)rgb[i]);
+}
+int orc_scene_dialect(const orc_scene* s) { return s->dialect; }
 
 /* ------------------------------------------------------------------ batch entry points */
 void orc_scene_info(const orc_scene* s, uint32_t out[8]) {

@@ -27,6 +27,17 @@ typedef struct orc_scene orc_scene;
 orc_scene* orc_scene_load(const char* path);
 orc_scene* orc_scene_parse(const char* text, long len);
 void orc_scene_free(orc_scene* s);
+/* The four earlier snapshots of the renderer (/root/reference/hw1..hw4/src/scene.cpp): dialect 1..4 selects that
+   snapshot's scene vocabulary, its Scene::RayIntersection (a loop over all primitives in file order) and its
+   Scene::RayTrace: 1 ray casting in double, 2 Whitted with point / directional lights, 3 path tracing with
+   uniform-hemisphere sampling, 4 = hw5's estimator without triangles and BVH.  orc_render_sum on a dialect 1 / 2
+   scene returns the deterministic frame (linear colour, once).  Pinned by tests/golden/hw*_*.npz (images of the
+   compiled reference programs); known deviation: primitives are rotated with glm's float quaternion-vector
+   product as in hw4/hw5, hw1..hw3 use a double-precision sandwich product (identical for unit quaternions). */
+orc_scene* orc_scene_load_dialect(const char* path, int dialect);
+orc_scene* orc_scene_parse_dialect(const char* text, long len, int dialect);
+int orc_scene_dialect(const orc_scene* s);
+void orc_flat_u8(long npix, const float* rgb_linear, uint8_t* out);
 
 /* header values */
 void orc_scene_info(const orc_scene* s, uint32_t out[8]);

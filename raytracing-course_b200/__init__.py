@@ -35,6 +35,9 @@ _SIGNATURES = {
     "rtc_device_count": (C.c_int, []),
     "rtc_scene_load": (C.c_void_p, [C.c_char_p, C.c_int]),
     "rtc_scene_parse": (C.c_void_p, [C.c_char_p, C.c_long, C.c_int]),
+    "rtc_scene_load_dialect": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int]),
+    "rtc_scene_parse_dialect": (C.c_void_p, [C.c_char_p, C.c_long, C.c_int, C.c_int]),
+    "rtc_scene_dialect": (C.c_int, [C.c_void_p]),
     "rtc_scene_free": (None, [C.c_void_p]),
     "rtc_scene_upload": (C.c_int, [C.c_void_p, _u64]),
     "rtc_scene_info": (C.c_int, [C.c_void_p, _u32]),
@@ -157,13 +160,15 @@ class Distribution:
 class Scene:
     """Scene (include/scene.h:58-90): Load + InitScene happen in the constructor."""
 
-    def __init__(self, path=None, text=None, device=0):
+    def __init__(self, path=None, text=None, device=0, dialect=5):
+        """dialect 1..5: the homework snapshot whose scene vocabulary and Scene::RayTrace apply (5 = hw5)."""
         self.lib = load_library()
+        self.dialect = dialect
         if path is not None:
-            self.h = self.lib.rtc_scene_load(os.fsencode(path), device)
+            self.h = self.lib.rtc_scene_load_dialect(os.fsencode(path), device, dialect)
         elif text is not None:
             raw = text.encode() if isinstance(text, str) else bytes(text)
-            self.h = self.lib.rtc_scene_parse(raw, len(raw), device)
+            self.h = self.lib.rtc_scene_parse_dialect(raw, len(raw), device, dialect)
         else:
             raise ValueError("path or text required")
         if not self.h:
@@ -174,8 +179,8 @@ class Scene:
         self._refresh()
 
     @classmethod
-    def Load(cls, path, device=0):
-        return cls(path=path, device=device)
+    def Load(cls, path, device=0, dialect=5):
+        return cls(path=path, device=device, dialect=dialect)
 
     def _refresh(self):
         info = np.zeros(8, np.uint32)

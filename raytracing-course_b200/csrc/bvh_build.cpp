@@ -362,6 +362,13 @@ void HostScene::init() {
         F.mat1[i] = f4{p.emission.x, p.emission.y, p.emission.z, p.ior};
     }
     F.lights = lights;
+    for (const PointLight& l : point_lights) {  // hw2: DirectedLight keeps glm::normalize(dir), hw2 src/lights.cpp:20-23
+        vec3 nd = l.directed ? normalize(l.dir) : mk3(0, 0, 0);
+        F.plights.push_back(pack(l.intensity, l.directed ? 1u : 0u));
+        F.plights.push_back(pack(l.pos, 0));
+        F.plights.push_back(pack(l.att, 0));
+        F.plights.push_back(pack(nd, 0));
+    }
     for (uint32_t i = nbvh; i < n; ++i) {  // planes sit behind the BVH primitives (src/scene.cpp:17-19)
         const Primitive& p = prims[i];
         bool rot_ident = p.rot.x == 0.f && p.rot.y == 0.f && p.rot.z == 0.f && p.rot.w == 1.f;

@@ -143,21 +143,8 @@ struct rtc_scene {
         S.geo0 = slices.geo0; S.geo1 = slices.geo1; S.geo2 = slices.geo2; S.xf_pos = slices.xf_pos; S.xf_rot = slices.xf_rot;
         S.mat0 = slices.mat0; S.mat1 = slices.mat1; S.inodes = slices.inodes; S.rnodes = slices.rnodes; S.rmeta = slices.rmeta;
         S.lca = slices.lca; S.lights = slices.lights; S.planes = slices.planes; S.ubox = slices.ubox;
-        S.nplanes = (uint32_t)(host.flat.planes.size() / 2);
-        S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
-        S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
-        S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;
-        S.width = host.cam.width; S.height = host.cam.height; S.ray_depth = host.ray_depth;
-        S.cam_pos = make_float3(host.cam.pos.x, host.cam.pos.y, host.cam.pos.z);
-        S.cam_right = make_float3(host.cam.right.x, host.cam.right.y, host.cam.right.z);
-        S.cam_up = make_float3(host.cam.up.x, host.cam.up.y, host.cam.up.z);
-        S.cam_forward = make_float3(host.cam.forward.x, host.cam.forward.y, host.cam.forward.z);
-        // Camera::GetToRay, src/scene.cpp:181-182 (tan evaluated in double, as the reference's
-        // unqualified tan() does; checked bit-exact against it in tests/)
-        float tx = (float)std::tan((double)(host.cam.fov_x / 2));
-        S.tan_fov_x = tx;
-        S.tan_fov_y = tx * (float)host.cam.height / (float)host.cam.width;
-        S.bg = make_float3(host.background.x, host.background.y, host.background.z);
+        S.plights = slices.plights;
+        fill_dev_scalars(host, S);
         return S;
     }
     void release_device() {
@@ -192,6 +179,7 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
         {F.rnodes.data(), F.rnodes.size() * sizeof(f4), 0}, {F.rmeta.data(), F.rmeta.size() * sizeof(u4), 0},
         {F.lca.data(), F.lca.size() * sizeof(uint32_t), 0}, {F.lights.data(), F.lights.size() * sizeof(int32_t), 0},
         {F.planes.data(), F.planes.size() * sizeof(f4), 0}, {F.ubox.data(), F.ubox.size() * sizeof(f4), 0},
+        {F.plights.data(), F.plights.size() * sizeof(f4), 0},
     };
     size_t total = 0, payload = 0;
     for (Part& p : parts) {
@@ -217,6 +205,7 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
         D.lca = (const uint32_t*)(base + parts[10].off); D.lights = (const int32_t*)(base + parts[11].off);
         D.planes = (const float4*)(base + parts[12].off);
         D.ubox = (const float4*)(base + parts[13].off);
+        D.plights = (const float4*)(base + parts[14].off);
     }
     CU(cudaMemcpyAsync(s->arena_dev, s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, nullptr));
     CU(cudaStreamSynchronize(nullptr));
@@ -230,9 +219,14 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
     return RTC_OK;
 }
 
-rtc_scene* make_scene(const std::string& text, int device) {
+rtc_scene* make_scene(const std::string& text, int device, int dialect = DIALECT_HW5) {
+    if (dialect < DIALECT_HW1 || dialect > DIALECT_HW5) {
+        fail(RTC_ERR_ARG, "dialect must be 1..5");
+        return nullptr;
+    }
     rtc_scene* s = new rtc_scene();
     try {
+        s->host.dialect = dialect;
         s->host.parse(text);
         s->host.init();
     } catch (const std::exception& e) {
@@ -242,6 +236,11 @@ rtc_scene* make_scene(const std::string& text, int device) {
     }
     if (s->host.ray_depth + 2 > (unsigned)kMaxDepthSlots) {
         fail(RTC_ERR_UNSUPPORTED, "RAY_DEPTH above 62 is not supported");
+        delete s;
+        return nullptr;
+    }
+    if (dialect == DIALECT_HW2 && s->host.ray_depth > 32) {
+        fail(RTC_ERR_UNSUPPORTED, "hw2 dialect: RAY_DEPTH above 32 is not supported");
         delete s;
         return nullptr;
     }
@@ -335,14 +334,20 @@ rtc_scene* rtc_scene_parse(const char* text, long len, int device) {
     if (!text || len < 0) { fail(RTC_ERR_ARG, "null scene text"); return nullptr; }
     return make_scene(std::string(text, (size_t)len), device);
 }
-rtc_scene* rtc_scene_load(const char* path, int device) {
+rtc_scene* rtc_scene_parse_dialect(const char* text, long len, int device, int dialect) {
+    if (!text || len < 0) { fail(RTC_ERR_ARG, "null scene text"); return nullptr; }
+    return make_scene(std::string(text, (size_t)len), device, dialect);
+}
+rtc_scene* rtc_scene_load_dialect(const char* path, int device, int dialect) {
     if (!path) { fail(RTC_ERR_ARG, "null path"); return nullptr; }
     std::ifstream in(path, std::ios::binary);
     if (!in) { fail(RTC_ERR_IO, std::string("cannot open scene file ") + path); return nullptr; }
     std::ostringstream ss;
     ss << in.rdbuf();
-    return make_scene(ss.str(), device);
+    return make_scene(ss.str(), device, dialect);
 }
+rtc_scene* rtc_scene_load(const char* path, int device) { return rtc_scene_load_dialect(path, device, DIALECT_HW5); }
+int rtc_scene_dialect(const rtc_scene* s) { return s ? s->host.dialect : 0; }
 void rtc_scene_free(rtc_scene* s) {
     if (!s) return;
     if (s->device >= 0) { cudaSetDevice(s->device); s->release_device(); }
@@ -547,6 +552,15 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     const uint64_t npix = (uint64_t)s->host.cam.width * s->host.cam.height;
     const uint64_t total = npix * sample_count;
     if (total == 0) return RTC_OK;
+    if (s->host.dialect <= DIALECT_HW2) {
+        // hw1 / hw2: one deterministic frame, whatever the sample range (the colour is added once)
+        LaunchCtx c{(cudaStream_t)stream, s->sms};
+        if (s->host.dialect == DIALECT_HW1) launch_raycast_hw1(c, s->dev(), accum_dev);
+        else launch_whitted_hw2(c, s->dev(), accum_dev);
+        s->launches++;
+        CU(cudaGetLastError());
+        return RTC_OK;
+    }
     const uint32_t depth = s->host.ray_depth;
     // batch size: the configured one, but small enough that every lane gets a batch (overlap matters
     // more than batch size: profiles/r01_experiments.md), rounded up to whole warps
@@ -628,7 +642,8 @@ int rtc_render_resolve(rtc_scene* s, const float* accum_dev, uint32_t total_samp
     if (!accum_dev || !rgb_dev || total_samples == 0) return fail(RTC_ERR_ARG, "bad argument");
     LaunchCtx c{(cudaStream_t)stream, s->sms};
     uint32_t nvalues = 3u * s->host.cam.width * s->host.cam.height;
-    launch_resolve(c, accum_dev, 1.f / (float)total_samples, nvalues, rgb_dev);  // 1.f / samples * sum, src/scene.cpp:201
+    if (s->host.dialect == DIALECT_HW1) launch_resolve_flat(c, accum_dev, 1.f / (float)total_samples, nvalues, rgb_dev);
+    else launch_resolve(c, accum_dev, 1.f / (float)total_samples, nvalues, rgb_dev);  // 1.f / samples * sum, src/scene.cpp:201
     s->launches++;
     CU(cudaGetLastError());
     return RTC_OK;
@@ -648,13 +663,14 @@ int rtc_render_u8(rtc_scene* s, uint32_t seed, uint8_t* rgb_host) {
     int rc = need_device(s);
     if (rc) return rc;
     if (!rgb_host) return fail(RTC_ERR_ARG, "null argument");
-    if (s->host.samples == 0) return fail(RTC_ERR_ARG, "scene has SAMPLES 0");
+    const uint32_t samples = s->host.dialect <= DIALECT_HW2 ? 1u : s->host.samples;  // hw1 / hw2 have no SAMPLES
+    if (samples == 0) return fail(RTC_ERR_ARG, "scene has SAMPLES 0");
     size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
     CU(s->accum.ensure(nvalues));
     CU(s->rgb.ensure(nvalues));
     CU(cudaMemsetAsync(s->accum.p, 0, nvalues * sizeof(float), nullptr));
-    if ((rc = rtc_render_accumulate(s, seed, 0, s->host.samples, s->accum.p, nullptr))) return rc;
-    if ((rc = rtc_render_resolve(s, s->accum.p, s->host.samples, s->rgb.p, nullptr))) return rc;
+    if ((rc = rtc_render_accumulate(s, seed, 0, samples, s->accum.p, nullptr))) return rc;
+    if ((rc = rtc_render_resolve(s, s->accum.p, samples, s->rgb.p, nullptr))) return rc;
     CU(cudaMemcpy(rgb_host, s->rgb.p, nvalues, cudaMemcpyDeviceToHost));
     return RTC_OK;
 }

@@ -2,7 +2,10 @@
 // BY VALUE as a kernel parameter (lives in the constant bank, no extra load to reach a pointer).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+
+#include "scene_host.h"
 
 namespace rtc {
 
@@ -24,13 +27,44 @@ struct DevScene {
     const int32_t* lights;
     const float4* ubox;    // per primitive slot: exact (min) (max) of the reference leaf that starts there
     const float4* planes;  // per plane: (n.xyz, bits(prim id)) (pos.xyz, bits(1 = no rotation))
+    const float4* plights; // hw2 dialect: 4 float4 per light (intensity, bits(directed)) (pos) (attenuation) (unit dir)
 
     uint32_t nprims, nbvh, nnodes, root, iroot, lca_levels, nlights, ref_depth;
     uint32_t width, height, ray_depth, nplanes;
     float3 cam_pos, cam_right, cam_up, cam_forward;
     float tan_fov_x, tan_fov_y;
     float3 bg;
+    // homework dialect (scene_host.h Dialect) and the constants that differ between the snapshots
+    uint32_t dialect, nplights;
+    float eps;         // ray offset: 1e-3 in hw2/hw3 (include/scene.h:60), 1e-4 in hw4/hw5
+    float plane_tmax;  // IntersectPlane drops t > 1e5 from hw4 on (hw4 src/primitives.cpp:47); earlier: no limit
+    float3 ambient;    // hw2 AMBIENT_LIGHT
 };
+
+// Every scalar of DevScene from the host scene (the array pointers are the caller's: HBM slices in c_api.cu,
+// host vectors in the test-only host emulation).
+inline void fill_dev_scalars(const HostScene& host, DevScene& S) {
+    S.nplanes = (uint32_t)(host.flat.planes.size() / 2);
+    S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
+    S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
+    S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;
+    S.width = host.cam.width; S.height = host.cam.height; S.ray_depth = host.ray_depth;
+    S.cam_pos = make_float3(host.cam.pos.x, host.cam.pos.y, host.cam.pos.z);
+    S.cam_right = make_float3(host.cam.right.x, host.cam.right.y, host.cam.right.z);
+    S.cam_up = make_float3(host.cam.up.x, host.cam.up.y, host.cam.up.z);
+    S.cam_forward = make_float3(host.cam.forward.x, host.cam.forward.y, host.cam.forward.z);
+    // Camera::GetToRay, src/scene.cpp:181-182 (tan evaluated in double, as the reference's
+    // unqualified tan() does; checked bit-exact against it in tests/)
+    float tx = (float)tan((double)(host.cam.fov_x / 2));
+    S.tan_fov_x = tx;
+    S.tan_fov_y = tx * (float)host.cam.height / (float)host.cam.width;
+    S.bg = make_float3(host.background.x, host.background.y, host.background.z);
+    S.nplights = (uint32_t)host.point_lights.size();
+    S.dialect = (uint32_t)host.dialect;
+    S.eps = host.dialect <= DIALECT_HW3 ? 1e-3f : 1e-4f;           // hwN include/scene.h `eps`
+    S.plane_tmax = host.dialect <= DIALECT_HW3 ? 3.0e38f : 1e5f;   // hw4 src/primitives.cpp:47
+    S.ambient = make_float3(host.ambient.x, host.ambient.y, host.ambient.z);
+}
 
 // wavefront path state, structure of float4 arrays
 struct PathSoA {

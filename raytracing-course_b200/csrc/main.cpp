@@ -2,8 +2,12 @@
 // (src/main.cpp:6-19, run.sh) on top of the C-ABI.  Extra, optional environment knobs:
 //   RTC_DEVICE=<n>   CUDA device (default 0)      RTC_SEED=<n>   RNG seed (default 0)
 //   RTC_SAMPLES / RTC_WIDTH / RTC_HEIGHT / RTC_RAY_DEPTH   override the scene file
+// The same program serves the four earlier homework snapshots (hwN/run.sh -> build/raytracing_hwN): the dialect
+// is the digit in the name it is called by (raytracing_hw1 .. raytracing_hw4 are links to this binary), or
+// RTC_DIALECT=<1..5>.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "rtc_b200.h"
 
@@ -17,7 +21,12 @@ int main(int argc, const char* argv[]) {
         std::fprintf(stderr, "usage: %s <scene.txt> <out.ppm>\n", argv[0]);
         return 2;
     }
-    rtc_scene* scene = rtc_scene_load(argv[1], env_int("RTC_DEVICE", 0));
+    int dialect = RTC_DIALECT_HW5;
+    const char* base = std::strrchr(argv[0], '/');
+    base = base ? base + 1 : argv[0];
+    if (std::strncmp(base, "raytracing_hw", 13) == 0 && base[13] >= '1' && base[13] <= '5' && base[14] == 0) dialect = base[13] - '0';
+    dialect = env_int("RTC_DIALECT", dialect);
+    rtc_scene* scene = rtc_scene_load_dialect(argv[1], env_int("RTC_DEVICE", 0), dialect);
     if (!scene) {
         std::fprintf(stderr, "raytracing_hw5: %s\n", rtc_last_error());
         return 1;

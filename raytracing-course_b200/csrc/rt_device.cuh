@@ -16,7 +16,6 @@ namespace rtc {
 #define RT_D __device__ __forceinline__
 
 constexpr float kInfF = 1e18f;      // include/bvh.h:9
-constexpr float kSceneEps = 1e-4f;  // include/scene.h:64
 constexpr float kPi = 3.14159274101257324f;  // (float)acos(-1), include/distributions.h:14
 constexpr int kRejectCap = 64;      // light sampling retries (the reference retries forever)
 constexpr int kMaxRecords = 24;     // leaf hits kept per ray before falling back to the reference tree walk
@@ -84,10 +83,10 @@ struct Isect {
 };
 
 // Primitive::IntersectPlane, src/primitives.cpp:55-66
-RT_D bool isect_plane(vec3 o, vec3 d, vec3 n, Isect& out) {
+RT_D bool isect_plane(vec3 o, vec3 d, vec3 n, float tmax, Isect& out) {
     float dn = dot(d, n);
     float t = -dot(o, n) / dn;
-    if (t > 1e5f) return false;
+    if (t > tmax) return false;
     if (t > 0.f) {
         out.t = t;
         out.interior = dn >= 0.f;
@@ -210,7 +209,7 @@ RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t)
     switch (flags & PF_TYPE_MASK) {
         case PT_BOX: ok = isect_box<FAST>(o, d, ld3(g0), is); break;
         case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), is); break;
-        default: ok = isect_plane(o, d, ld3(g0), is); break;
+        default: ok = isect_plane(o, d, ld3(g0), S.plane_tmax, is); break;
     }
     t = is.t;
     return ok;
@@ -234,7 +233,7 @@ RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect
         }
         case PT_BOX: ok = isect_box<FAST>(o, d, ld3(g0), out); break;
         case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), out); break;
-        default: ok = isect_plane(o, d, ld3(g0), out); break;
+        default: ok = isect_plane(o, d, ld3(g0), S.plane_tmax, out); break;
     }
     if (!ok) return false;
     if (!(flags & PF_ROT_IDENT)) {
@@ -563,12 +562,12 @@ RT_D void closest_plane(const DevScene& S, vec3 o, vec3 d, float& closest, int& 
         if (__float_as_uint(b.w)) {
             vec3 n = ld3(a);
             t = -dot(o - ld3(b), n) / dot(d, n);
-            ok = t > 0.f && !(t > 1e5f);
+            ok = t > 0.f && !(t > S.plane_tmax);
         } else {  // rotated plane: ray into the plane's frame (src/primitives.cpp:15), plane code only
             vec3 lo = o, ld = d;
             to_local(S, prim, prim_flags(S, prim), lo, ld);
             Isect is;
-            ok = isect_plane(lo, ld, ld3(a), is);
+            ok = isect_plane(lo, ld, ld3(a), S.plane_tmax, is);
             t = is.t;
         }
         if (ok && t < closest) { closest = t; id = (int)prim; }

@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, HitSoA 
             Rng g{seed, pixel, sample, 0};
             uint4 b = g.block(0);
             float fx = __fadd_rn((float)x, u01(b.x)), fy = __fadd_rn((float)y, u01(b.y));
+            // hw3's Camera::GetToRay(float, float) still adds the half pixel of its integer ancestor
+            // (hw3 src/scene.cpp:186-187): its jittered samples cover [x + 0.5, x + 1.5)
+            if (S.dialect == DIALECT_HW3) { fx = __fadd_rn(fx, 0.5f); fy = __fadd_rn(fy, 0.5f); }
             vec3 o, d;
             camera_ray(S, fx, fy, o, d);
             P.o[i] = make_float4(o.x, o.y, o.z, 0.f);
@@ -285,12 +288,16 @@ RT_D void deposit(float* accum, uint32_t pixel, vec3 L) {
 #define RTC_SHADE_THREADS 128   // 128 x 6 blocks/SM (80 registers, 76 B spills) measured best: profiles/r01_experiments.md
 #define RTC_SHADE_MIN_BLOCKS 6
 #endif
+// HW3 = the hw3 snapshot's diffuse term (hw3 src/scene.cpp:238-249): a direction uniform on the hemisphere
+// around the normal, weight 2 C cos; every other line of the switch is common to hw3, hw4 and hw5.
+template <bool HW3>
 __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                                                 uint32_t* qout, uint32_t* tq, uint32_t* tq_count, float* accum, uint32_t bounce,
                                                 uint32_t seed) {
     const uint32_t count = *qin;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t rounded = (count + 31u) & ~31u;
+    const float eps = S.eps;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool alive = false;
         vec3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0), beta = mk3(0, 0, 0), L = mk3(0, 0, 0);
@@ -314,8 +321,15 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
                 uint32_t material = __float_as_uint(m0.w);
                 if (bounce < S.ray_depth) {
                     Rng g{seed, pixel, sample, bounce};
-                    if (material == MAT_DIFFUSE) {
-                        vec3 p_outer = p + kSceneEps * normal;
+                    if (HW3 && material == MAT_DIFFUSE) {
+                        vec3 dir = normal_vec(g.block(1));
+                        float cs = dot(dir, normal);
+                        if (cs < 0.f) { dir = -dir; cs = -cs; }
+                        beta = beta * mk3(col.x * (2.f * cs), col.y * (2.f * cs), col.z * (2.f * cs));
+                        no = p + eps * dir; nd = dir;
+                        alive = true;
+                    } else if (material == MAT_DIFFUSE) {
+                        vec3 p_outer = p + eps * normal;
                         vec3 dir = mix_sample(S, g, p_outer, normal);
                         float cs = dot(dir, normal);
                         if (cs > 0.f) {
@@ -324,13 +338,13 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
                             vec3 w = mk3(col.x * inv_pi, col.y * inv_pi, col.z * inv_pi);
                             float k2 = __fdividef(1.f, pw);
                             beta = beta * mk3(w.x * cs * k2, w.y * cs * k2, w.z * cs * k2);
-                            no = p + kSceneEps * dir; nd = dir;
+                            no = p + eps * dir; nd = dir;
                             alive = true;
                         }
                     } else if (material == MAT_METALLIC) {
                         vec3 rd = reflect_dir(normal, normalize(d));
                         beta = beta * col;
-                        no = p + kSceneEps * rd; nd = rd;
+                        no = p + eps * rd; nd = rd;
                         alive = true;
                     } else {  // DIELECTRIC, src/scene.cpp:130-170
                         float eta1 = 1.f, eta2 = m1.w;
@@ -350,12 +364,12 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
                         }
                         if (reflect) {
                             vec3 rd = reflect_dir(normal, nd_in);
-                            no = p + kSceneEps * rd; nd = rd;
+                            no = p + eps * rd; nd = rd;
                         } else {
                             float cos2 = sqrtf(1.f - sin2 * sin2);
                             float e = eta1 / eta2;
                             vec3 fr = e * (-dir) + (e * dn - cos2) * normal;
-                            no = p + kSceneEps * fr; nd = fr;
+                            no = p + eps * fr; nd = fr;
                             if (!interior) beta = beta * col;
                         }
                         alive = true;
@@ -515,7 +529,9 @@ void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, Hit
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                   uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float* accum, uint32_t bounce,
                   uint32_t seed) {
-    k_shade<<<grid_for(max_count, RTC_SHADE_THREADS, c.sms, 2048 / RTC_SHADE_THREADS), RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
+    const int grid = grid_for(max_count, RTC_SHADE_THREADS, c.sms, 2048 / RTC_SHADE_THREADS);
+    if (S.dialect == DIALECT_HW3) k_shade<true><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
+    else k_shade<false><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
 }
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     k_tally<<<1, 1, 0, c.stream>>>(q, tqc, ray_depth, stats);

@@ -39,4 +39,9 @@ void launch_pdf_batch(const LaunchCtx& c, const DevScene& S, long n, const float
 void launch_sample_batch(const LaunchCtx& c, const DevScene& S, long n, const float* x, const float* nr, uint32_t seed,
                          uint32_t sample, uint32_t bounce, float* dir);
 
+// course_kernels.cu: the deterministic dialects, one launch per frame, colour ADDED into accum (3 floats per pixel)
+void launch_raycast_hw1(const LaunchCtx& c, const DevScene& S, float* accum);
+void launch_whitted_hw2(const LaunchCtx& c, const DevScene& S, float* accum);
+void launch_resolve_flat(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out);
+
 }  // namespace rtc

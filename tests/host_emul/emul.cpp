@@ -57,19 +57,9 @@ void* emu_scene_load(const char* path) {
     S.inodes = (const float4*)F.inodes.data(); S.rnodes = (const float4*)F.rnodes.data();
     S.rmeta = (const uint4*)F.rmeta.data(); S.lca = F.lca.data(); S.lights = F.lights.data();
     S.ubox = (const float4*)F.ubox.data();
-    S.planes = (const float4*)F.planes.data(); S.nplanes = (uint32_t)(F.planes.size() / 2);
-    S.nprims = (uint32_t)e->host.prims.size(); S.nbvh = e->host.nbvh; S.nnodes = (uint32_t)e->host.nodes.size();
-    S.root = e->host.root; S.iroot = F.iroot; S.lca_levels = F.lca_levels; S.nlights = (uint32_t)e->host.lights.size();
-    S.ref_depth = F.ref_depth;
-    S.width = e->host.cam.width; S.height = e->host.cam.height; S.ray_depth = e->host.ray_depth;
-    S.cam_pos = make_float3(e->host.cam.pos.x, e->host.cam.pos.y, e->host.cam.pos.z);
-    S.cam_right = make_float3(e->host.cam.right.x, e->host.cam.right.y, e->host.cam.right.z);
-    S.cam_up = make_float3(e->host.cam.up.x, e->host.cam.up.y, e->host.cam.up.z);
-    S.cam_forward = make_float3(e->host.cam.forward.x, e->host.cam.forward.y, e->host.cam.forward.z);
-    float tx = (float)tan((double)(e->host.cam.fov_x / 2));
-    S.tan_fov_x = tx;
-    S.tan_fov_y = tx * (float)e->host.cam.height / (float)e->host.cam.width;
-    S.bg = make_float3(e->host.background.x, e->host.background.y, e->host.background.z);
+    S.planes = (const float4*)F.planes.data();
+    S.plights = (const float4*)F.plights.data();
+    fill_dev_scalars(e->host, S);
     return e;
 }
 void emu_scene_free(void* h) { delete (EmuScene*)h; }

@@ -53,6 +53,11 @@ class _Lib:
         if pfx == "orc_":
             L.orc_scene_parse.restype = C.c_void_p
             L.orc_scene_parse.argtypes = [C.c_char_p, C.c_long]
+            L.orc_scene_load_dialect.restype = C.c_void_p
+            L.orc_scene_load_dialect.argtypes = [C.c_char_p, C.c_int]
+            L.orc_scene_parse_dialect.restype = C.c_void_p
+            L.orc_scene_parse_dialect.argtypes = [C.c_char_p, C.c_long, C.c_int]
+            L.orc_flat_u8.argtypes = [C.c_long, f32p, u8p]
             L.orc_scene_prim_order.argtypes = [C.c_void_p, i32p]
             L.orc_scene_camera.argtypes = [C.c_void_p, f32p]
             L.orc_mix_sample.argtypes = [C.c_void_p, C.c_long, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
@@ -75,11 +80,18 @@ class _Lib:
 class Scene:
     """A loaded scene on either backend with numpy-in / numpy-out batch calls."""
 
-    def __init__(self, backend, path):
+    def __init__(self, backend, path=None, dialect=5, text=None):
         self.b = backend
-        self.h = backend.fn("scene_load")(os.fsencode(path))
+        self.dialect = dialect
+        if text is not None:
+            raw = text.encode() if isinstance(text, str) else bytes(text)
+            self.h = backend.lib.orc_scene_parse_dialect(raw, len(raw), dialect)
+        elif dialect != 5:
+            self.h = backend.lib.orc_scene_load_dialect(os.fsencode(path), dialect)
+        else:
+            self.h = backend.fn("scene_load")(os.fsencode(path))
         if not self.h:
-            raise IOError("cannot load scene " + path)
+            raise IOError("cannot load scene " + str(path))
         info = np.zeros(8, np.uint32)
         backend.fn("scene_info")(self.h, info)
         (self.width, self.height, self.ray_depth, self.samples,
@@ -146,6 +158,18 @@ class Scene:
         return out
 
     # oracle only -----------------------------------------------------------
+    def frame_u8(self, seed=0, nthreads=0):
+        """Scene::Render of the scene's dialect: (H, W, 3) uint8 (hw1: colours as they are; else ACES + gamma)."""
+        spp = 1 if self.dialect <= 2 else self.samples
+        s, _, _ = self.render_sum(seed, 0, spp, nthreads=nthreads)
+        mean = np.ascontiguousarray(s * np.float32(1.0 / spp))
+        out = np.zeros(mean.shape, np.uint8)
+        if self.dialect == 1:
+            self.b.lib.orc_flat_u8(mean.shape[0], mean, out)
+        else:
+            self.b.lib.orc_tonemap_u8(mean.shape[0], mean, out)
+        return out.reshape(self.height, self.width, 3)
+
     def prim_order(self):
         out = np.zeros(self.nprims, np.int32)
         self.b.lib.orc_scene_prim_order(self.h, out)
@@ -205,6 +229,34 @@ def ref():
     if _ref is None:
         _ref = _Lib(REFPROBE_SO, "ref_")
     return _ref
+
+
+def ref_dialect_bin(dialect):
+    """oracle/_ref/raytracing_hwN: the unmodified reference program of that snapshot (oracle/Makefile)."""
+    return os.path.join(ORACLE_DIR, "_ref", "raytracing_hw%d" % dialect)
+
+
+def read_ppm(path):
+    raw = open(path, "rb").read()
+    magic, dims, maxv, body = raw.split(b"\n", 3)
+    w, h = [int(v) for v in dims.split()]
+    assert magic == b"P6" and maxv == b"255"
+    return np.frombuffer(body, np.uint8, count=3 * w * h).reshape(h, w, 3)
+
+
+def with_header(text, width=None, height=None, samples=None, ray_depth=None):
+    """Scene text with DIMENSIONS / SAMPLES / RAY_DEPTH lines replaced (the reference programs take no overrides)."""
+    out = []
+    for line in text.splitlines():
+        word = line.split()[0] if line.split() else ""
+        if word == "DIMENSIONS" and width is not None:
+            line = "DIMENSIONS %d %d" % (width, height)
+        elif word == "SAMPLES" and samples is not None:
+            line = "SAMPLES %d" % samples
+        elif word == "RAY_DEPTH" and ray_depth is not None:
+            line = "RAY_DEPTH %d" % ray_depth
+        out.append(line)
+    return "\n".join(out) + "\n"
 
 
 def pixel_center_rays(scene, step=1):

@@ -117,6 +117,23 @@ def render_fixture(name, width, height, samples, ray_depth=-1):
     s.close()
 
 
+def dialect_fixture(dialect, name, width=None, height=None, samples=None):
+    """Image written by the unmodified hwN program (oracle/_ref/raytracing_hwN, built by oracle/Makefile from
+    /root/reference/hwN) for scenes/<name>.txt with the header lines replaced; the fixture keeps the exact scene
+    text next to the 8-bit image, so a checker needs neither the scene file nor the reference."""
+    import subprocess
+    import tempfile
+    text = orclib.with_header(open(os.path.join(SCENES, name + ".txt")).read(), width, height, samples)
+    with tempfile.TemporaryDirectory() as td:
+        sp, op = os.path.join(td, "scene.txt"), os.path.join(td, "out.ppm")
+        open(sp, "w").write(text)
+        subprocess.run([orclib.ref_dialect_bin(dialect), sp, op], check=True, stderr=subprocess.DEVNULL)
+        img = orclib.read_ppm(op).copy()
+    out = "hw%d_%s.npz" % (dialect, name)
+    np.savez_compressed(os.path.join(GOLD, out), u8=img, text=np.frombuffer(text.encode(), np.uint8), dialect=dialect)
+    print(out, img.shape, "mean", img.mean(axis=(0, 1)).round(2))
+
+
 def sort_fixture():
     """std::sort / std::partition permutations on keys with many ties (what the BVH order hinges on)."""
     rng = np.random.default_rng(11)
@@ -188,7 +205,22 @@ def main():
     render_fixture("rabbid", 88, 88, 256)
     for sfx in ("", "_glass", "_metal"):
         render_fixture("practice5_dragon_100k" + sfx, 48, 48, 128)
+    dialects()
+
+
+def dialects():
+    """The four earlier snapshots only write images: deterministic ones at the scene's own size, Monte Carlo
+    ones converged at a reduced size."""
+    dialect_fixture(1, "course_sample6")
+    dialect_fixture(2, "hw2_lights")
+    dialect_fixture(3, "course_sample6", 103, 133, 2048)
+    dialect_fixture(4, "course_sample6", 103, 133, 2048)
+    dialect_fixture(3, "course_sample4", 64, 64, 4096)
+    dialect_fixture(4, "course_sample4", 64, 64, 2048)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "dialects":
+        dialects()
+    else:
+        main()

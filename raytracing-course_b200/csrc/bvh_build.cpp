@@ -344,6 +344,9 @@ void HostScene::init() {
         bool pos_zero = p.pos.x == 0.f && p.pos.y == 0.f && p.pos.z == 0.f;
         if (rot_ident) flags |= PF_ROT_IDENT;
         if (rot_ident && pos_zero) flags |= PF_IDENT;
+        if (!rot_ident) F.features |= FE_ROTATION;
+        if (p.type == PT_ELLIPSOID) F.features |= FE_ELLIPSOID;
+        if (p.material != MAT_DIFFUSE) F.features |= FE_SPECULAR;
         if (p.type == PT_TRIANGLE) {
             // n = normalize(cross(b - a, c - a)), src/primitives.cpp:156 -- same float operations,
             // evaluated once here instead of once per intersection test

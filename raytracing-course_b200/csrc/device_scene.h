@@ -36,6 +36,7 @@ struct DevScene {
     float3 bg;
     // homework dialect (scene_host.h Dialect) and the constants that differ between the snapshots
     uint32_t dialect, nplights;
+    uint32_t features;  // SceneFeature bits (scene_host.h): which instantiation of k_shade covers the scene
     float eps;         // ray offset: 1e-3 in hw2/hw3 (include/scene.h:60), 1e-4 in hw4/hw5
     float plane_tmax;  // IntersectPlane drops t > 1e5 from hw4 on (hw4 src/primitives.cpp:47); earlier: no limit
     float3 ambient;    // hw2 AMBIENT_LIGHT
@@ -61,6 +62,7 @@ inline void fill_dev_scalars(const HostScene& host, DevScene& S) {
     S.bg = make_float3(host.background.x, host.background.y, host.background.z);
     S.nplights = (uint32_t)host.point_lights.size();
     S.dialect = (uint32_t)host.dialect;
+    S.features = host.flat.features;
     S.eps = host.dialect <= DIALECT_HW3 ? 1e-3f : 1e-4f;           // hwN include/scene.h `eps`
     S.plane_tmax = host.dialect <= DIALECT_HW3 ? 3.0e38f : 1e5f;   // hw4 src/primitives.cpp:47
     S.ambient = make_float3(host.ambient.x, host.ambient.y, host.ambient.z);

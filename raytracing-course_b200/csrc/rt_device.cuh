@@ -193,6 +193,18 @@ RT_D void to_local(const DevScene& S, uint32_t prim, uint32_t flags, vec3& o, ve
 }
 RT_D uint32_t prim_flags(const DevScene& S, uint32_t prim) { return __float_as_uint(__ldg(&S.xf_pos[prim].w)); }
 
+// Scene features (scene_host.h SceneFeature, DevScene::features): k_shade is instruction-cache bound, so it is
+// compiled once per feature set and the host picks the smallest instantiation that covers the scene.  A kernel
+// built WITHOUT a feature is only ever launched on scenes that do not have it; what it computes for the
+// primitives that remain is the same arithmetic as the full version (the rotation code is already skipped per
+// primitive through PF_ROT_IDENT, the type switches lose a case).
+template <uint32_t FEAT>
+RT_D uint32_t prim_flags_for(const DevScene& S, uint32_t prim) {
+    uint32_t flags = prim_flags(S, prim);
+    if (!(FEAT & FE_ROTATION)) flags |= PF_ROT_IDENT;
+    return flags;
+}
+
 // distance-only test used during traversal (normal is recomputed once for the winner)
 template <bool FAST = false>
 RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t) {
@@ -215,25 +227,26 @@ RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t)
     return ok;
 }
 // Primitive::Intersect, src/primitives.cpp:14-52 (normal back to world space, re-normalised)
-template <bool FAST = false>
+template <bool FAST = false, uint32_t FEAT = FE_ALL>
 RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect& out) {
-    uint32_t flags = prim_flags(S, prim);
+    uint32_t flags = prim_flags_for<FEAT>(S, prim);
     to_local(S, prim, flags, o, d);
     float4 g0 = ldg4(S.geo0 + prim);
     bool ok;
-    switch (flags & PF_TYPE_MASK) {
-        case PT_TRIANGLE: {
-            float4 g1 = ldg4(S.geo1 + prim), g2 = ldg4(S.geo2 + prim);
-            vec3 n = mk3(g0.w, g1.w, g2.w);
-            bool interior;
-            ok = isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), n, out.t, interior);
-            out.interior = interior;
-            out.n = interior ? -n : n;
-            break;
-        }
-        case PT_BOX: ok = isect_box<FAST>(o, d, ld3(g0), out); break;
-        case PT_ELLIPSOID: ok = isect_ellipsoid(o, d, ld3(g0), out); break;
-        default: ok = isect_plane(o, d, ld3(g0), S.plane_tmax, out); break;
+    const uint32_t type = flags & PF_TYPE_MASK;
+    if (type == PT_TRIANGLE) {
+        float4 g1 = ldg4(S.geo1 + prim), g2 = ldg4(S.geo2 + prim);
+        vec3 n = mk3(g0.w, g1.w, g2.w);
+        bool interior;
+        ok = isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), n, out.t, interior);
+        out.interior = interior;
+        out.n = interior ? -n : n;
+    } else if (type == PT_BOX) {
+        ok = isect_box<FAST>(o, d, ld3(g0), out);
+    } else if ((FEAT & FE_ELLIPSOID) && type == PT_ELLIPSOID) {
+        ok = isect_ellipsoid(o, d, ld3(g0), out);
+    } else {
+        ok = isect_plane(o, d, ld3(g0), S.plane_tmax, out);
     }
     if (!ok) return false;
     if (!(flags & PF_ROT_IDENT)) {
@@ -551,6 +564,7 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
 // Closest plane (planes are stored last and are not part of the BVH), src/scene.cpp:50-66.
 // Planes without rotation use the world-space form t = -dot(o - pos, n) / dot(d, n), which is
 // what Primitive::Intersect + IntersectPlane evaluate for an identity rotator.
+template <uint32_t FEAT = FE_ALL>
 RT_D void closest_plane(const DevScene& S, vec3 o, vec3 d, float& closest, int& id) {
     closest = kInfF;
     id = -1;
@@ -559,7 +573,7 @@ RT_D void closest_plane(const DevScene& S, vec3 o, vec3 d, float& closest, int& 
         uint32_t prim = __float_as_uint(a.w);
         float t;
         bool ok;
-        if (__float_as_uint(b.w)) {
+        if (!(FEAT & FE_ROTATION) || __float_as_uint(b.w)) {
             vec3 n = ld3(a);
             t = -dot(o - ld3(b), n) / dot(d, n);
             ok = t > 0.f && !(t > S.plane_tmax);
@@ -611,11 +625,12 @@ RT_D SceneHit scene_intersect(const DevScene& S, vec3 o, vec3 d, uint32_t* visit
 
 // Primitive::Intersect restricted to what a light can be (box or ellipsoid): same arithmetic as
 // prim_intersect<true>, without the triangle / plane code (k_shade is instruction-cache bound).
+template <uint32_t FEAT = FE_ALL>
 RT_D bool light_intersect(const DevScene& S, uint32_t prim, bool is_box, vec3 o, vec3 d, Isect& out) {
-    uint32_t flags = prim_flags(S, prim);
+    uint32_t flags = prim_flags_for<FEAT>(S, prim);
     to_local(S, prim, flags, o, d);
     vec3 g0 = ld3(ldg4(S.geo0 + prim));
-    bool ok = is_box ? isect_box<true>(o, d, g0, out) : isect_ellipsoid(o, d, g0, out);
+    bool ok = (is_box || !(FEAT & FE_ELLIPSOID)) ? isect_box<true>(o, d, g0, out) : isect_ellipsoid(o, d, g0, out);
     if (!ok) return false;
     if (!(flags & PF_ROT_IDENT)) {
         float4 q4 = ldg4(S.xf_rot + prim);
@@ -636,10 +651,12 @@ RT_D vec3 sample_cosine(const Rng& g, vec3 n) {
     return normalize(dir);
 }
 // Distribution::SampleBox, src/distributions.cpp:227-269
+template <uint32_t FEAT = FE_ALL>
 RT_D vec3 sample_box(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
     vec3 s = ld3(ldg4(S.geo0 + prim));
     vec3 pos = ld3(ldg4(S.xf_pos + prim));
-    float4 q4 = ldg4(S.xf_rot + prim);
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (FEAT & FE_ROTATION) q4 = ldg4(S.xf_rot + prim);
     quat q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
     float wx = s.x * s.x, wy = s.y * s.y, wz = s.z * s.z;
     vec3 smp = mk3(0, 0, 0);
@@ -653,10 +670,10 @@ RT_D vec3 sample_box(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
         if (u < wx) pnt.x = side * s.x;
         else if (u < wx + wy) pnt.y = side * s.y;
         else pnt.z = side * s.z;
-        vec3 on_box = rotate(q, pnt) + pos;
+        vec3 on_box = ((FEAT & FE_ROTATION) ? rotate(q, pnt) : pnt) + pos;  // rotate(identity, v) == v exactly
         smp = normalize(on_box - x);
         Isect is;
-        if (light_intersect(S, prim, true, x, smp, is)) break;
+        if (light_intersect<FEAT>(S, prim, true, x, smp, is)) break;
     }
     return smp;
 }
@@ -677,6 +694,7 @@ RT_D vec3 sample_ellipsoid(const DevScene& S, uint32_t prim, const Rng& g, vec3 
     return smp;
 }
 // Distribution::SampleMix, src/distributions.cpp:385-399
+template <uint32_t FEAT = FE_ALL>
 RT_D vec3 mix_sample(const DevScene& S, const Rng& g, vec3 x, vec3 n) {
     uint4 b0 = g.block(0);
     float flip = u01(b0.x);
@@ -684,7 +702,7 @@ RT_D vec3 mix_sample(const DevScene& S, const Rng& g, vec3 x, vec3 n) {
     float fid = u01(b0.y);
     uint32_t id = (uint32_t)floorf(fid * (float)S.nlights);
     uint32_t prim = (uint32_t)__ldg(S.lights + id);
-    if ((prim_flags(S, prim) & PF_TYPE_MASK) == PT_BOX) return sample_box(S, prim, g, x);
+    if (!(FEAT & FE_ELLIPSOID) || (prim_flags(S, prim) & PF_TYPE_MASK) == PT_BOX) return sample_box<FEAT>(S, prim, g, x);
     return sample_ellipsoid(S, prim, g, x);
 }
 // PdfPointBox / PdfPointEllipsoid, src/distributions.cpp:271-287, 340-347
@@ -711,9 +729,10 @@ RT_D float pdf_point(const DevScene& S, uint32_t prim, bool is_box, float dist2,
 //    graze the ellipsoid the float discriminant b^2 - 4ac is cancellation noise, the reference's two
 //    roots are then off by ~1e-3 and its pdf several times smaller than the analytic value; a
 //    "cleaner" one-pass evaluation is measurably darker than the reference (4 sigma on lights_mix).
+template <uint32_t FEAT = FE_ALL>
 RT_D float pdf_light(const DevScene& S, uint32_t prim, vec3 x, vec3 d) {
-    const uint32_t flags = prim_flags(S, prim);
-    if ((flags & PF_TYPE_MASK) != PT_BOX) {
+    const uint32_t flags = prim_flags_for<FEAT>(S, prim);
+    if ((FEAT & FE_ELLIPSOID) && (flags & PF_TYPE_MASK) != PT_BOX) {
         Isect i1;
         if (!light_intersect(S, prim, false, x, d, i1)) return 1e-9f;
         if (i1.t <= 1e-8f) return 1e-9f;
@@ -761,11 +780,12 @@ RT_D float pdf_light(const DevScene& S, uint32_t prim, vec3 x, vec3 d) {
     return sum;
 }
 // Distribution::PdfMix, src/distributions.cpp:401-416
+template <uint32_t FEAT = FE_ALL>
 RT_D float mix_pdf(const DevScene& S, vec3 x, vec3 n, vec3 d) {
     float sum = fmaxf(0.f, 1.f / kPi * dot(d, n));
     if (S.nlights > 0) {
         float prim_sum = 0.f;
-        for (uint32_t i = 0; i < S.nlights; ++i) prim_sum += pdf_light(S, (uint32_t)__ldg(S.lights + i), x, d);
+        for (uint32_t i = 0; i < S.nlights; ++i) prim_sum += pdf_light<FEAT>(S, (uint32_t)__ldg(S.lights + i), x, d);
         prim_sum *= 1.f / (float)S.nlights;
         sum = 0.5f * sum + 0.5f * prim_sum;
     }

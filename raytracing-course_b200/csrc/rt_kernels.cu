@@ -21,9 +21,10 @@ constexpr uint32_t kChunk = 32;           // queue slots a warp reserves per ato
 // Planes (src/scene.cpp:50-66) and the root of the index BVH for one fresh ray: cd = closest_dist
 // handed to BVH_t::Intersect, id = the plane hit so far; returns whether the ray touches any
 // child box of the index root (only those rays are queued for k_traverse).
+template <uint32_t FEAT = FE_ALL>
 RT_D bool pre_step(const DevScene& S, vec3 o, vec3 d, float& cd, uint32_t& id) {
     int pid;
-    closest_plane(S, o, d, cd, pid);
+    closest_plane<FEAT>(S, o, d, cd, pid);
     id = pid < 0 ? HIT_MISS : (uint32_t)pid;
     if (S.iroot == IREF_NONE) return false;
     if (S.iroot & IREF_LEAF) {
@@ -290,7 +291,9 @@ RT_D void deposit(float* accum, uint32_t pixel, vec3 L) {
 #endif
 // HW3 = the hw3 snapshot's diffuse term (hw3 src/scene.cpp:238-249): a direction uniform on the hemisphere
 // around the normal, weight 2 C cos; every other line of the switch is common to hw3, hw4 and hw5.
-template <bool HW3>
+// FEAT = the scene features this instantiation supports (rt_device.cuh prim_flags_for): the kernel is bound by
+// instruction fetch, and the course's dragon scenes use a third of its code (no rotation, no ellipsoid, diffuse).
+template <bool HW3, uint32_t FEAT>
 __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                                                 uint32_t* qout, uint32_t* tq, uint32_t* tq_count, float* accum, uint32_t bounce,
                                                 uint32_t seed) {
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
             uint32_t prim = H.id[i];
             Isect is;
             vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
-            if (prim == HIT_MISS || !prim_intersect(S, prim, o, d, is)) {
+            if (prim == HIT_MISS || !prim_intersect<false, FEAT>(S, prim, o, d, is)) {
                 L = L + beta * mk3(S.bg.x, S.bg.y, S.bg.z);  // src/scene.cpp:92-94
             } else {
                 bool interior = is.interior != 0;
@@ -330,10 +333,10 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
                         alive = true;
                     } else if (material == MAT_DIFFUSE) {
                         vec3 p_outer = p + eps * normal;
-                        vec3 dir = mix_sample(S, g, p_outer, normal);
+                        vec3 dir = mix_sample<FEAT>(S, g, p_outer, normal);
                         float cs = dot(dir, normal);
                         if (cs > 0.f) {
-                            float pw = mix_pdf(S, p_outer, normal, dir);
+                            float pw = mix_pdf<FEAT>(S, p_outer, normal, dir);
                             const float inv_pi = 1.f / kPi;
                             vec3 w = mk3(col.x * inv_pi, col.y * inv_pi, col.z * inv_pi);
                             float k2 = __fdividef(1.f, pw);
@@ -341,6 +344,8 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
                             no = p + eps * dir; nd = dir;
                             alive = true;
                         }
+                    } else if (!(FEAT & FE_SPECULAR)) {
+                        // unreachable: the host launches this instantiation only for all-diffuse scenes
                     } else if (material == MAT_METALLIC) {
                         vec3 rd = reflect_dir(normal, normalize(d));
                         beta = beta * col;
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
                 N.rad[dst] = make_float4(L.x, L.y, L.z, __uint_as_float(sample));
                 // first part of the next Scene::RayIntersection, while the ray is still in registers
                 float cd; uint32_t id;
-                enters = pre_step(S, no, nd, cd, id);
+                enters = pre_step<FEAT>(S, no, nd, cd, id);
                 HN.cd[dst] = cd;
                 HN.id[dst] = id;
             }
@@ -530,8 +535,18 @@ void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, Pa
                   uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float* accum, uint32_t bounce,
                   uint32_t seed) {
     const int grid = grid_for(max_count, RTC_SHADE_THREADS, c.sms, 2048 / RTC_SHADE_THREADS);
-    if (S.dialect == DIALECT_HW3) k_shade<true><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
-    else k_shade<false><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed);
+#define RTC_SHADE(HW3, FEAT) k_shade<HW3, FEAT><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum, bounce, seed)
+    // the smallest instantiation that covers the scene's features (DevScene::features)
+#ifdef RTC_SHADE_NO_SPECIALISATION
+    const uint32_t feat = FE_ALL;
+#else
+    const uint32_t feat = S.features;
+#endif
+    if (S.dialect == DIALECT_HW3) RTC_SHADE(true, FE_ALL);
+    else if (feat == 0) RTC_SHADE(false, 0);
+    else if (feat == FE_SPECULAR) RTC_SHADE(false, FE_SPECULAR);
+    else RTC_SHADE(false, FE_ALL);
+#undef RTC_SHADE
 }
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     k_tally<<<1, 1, 0, c.stream>>>(q, tqc, ray_depth, stats);

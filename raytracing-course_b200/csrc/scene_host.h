@@ -44,6 +44,14 @@ enum PrimFlags : int {
     PF_ROT_IDENT = 1 << 5  // rot == identity (pos may be non-zero)
 };
 
+// what a scene contains, as far as the shading kernel's code size is concerned (rt_device.cuh prim_flags_for)
+enum SceneFeature : unsigned {
+    FE_ROTATION = 1,   // some primitive has a rotation other than identity
+    FE_ELLIPSOID = 2,  // some primitive (light or not) is an ellipsoid
+    FE_SPECULAR = 4,   // some primitive is METALLIC or DIELECTRIC
+    FE_ALL = 7
+};
+
 struct Primitive {
     int type = 0;
     int material = MAT_DIFFUSE;
@@ -99,6 +107,7 @@ struct FlatScene {
     std::vector<int32_t> lights;
     std::vector<f4> plights;           // hw2: 4 x f4 per light: (intensity, bits(directed)) (pos,0) (attenuation,0) (normalised dir,0)
     uint32_t index_depth = 0, ref_depth = 0, units = 0;
+    uint32_t features = 0;             // SceneFeature bits present in this scene
 };
 
 struct HostScene {

@@ -29,7 +29,7 @@ static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 #define __logf logf        /* glibc declares __logf / __sincosf itself: map the CUDA fast intrinsics by macro */
 #define __sincosf sincosf
 
-#include "rt_device.cuh"
+#include "course_device.cuh"
 
 using namespace rtc;
 
@@ -40,14 +40,16 @@ struct EmuScene {
 
 extern "C" {
 
-void* emu_scene_load(const char* path) {
-    std::ifstream in(path, std::ios::binary);
-    if (!in) return nullptr;
-    std::ostringstream ss;
-    ss << in.rdbuf();
+static void* emu_build(const std::string& text, int dialect) {
     EmuScene* e = new EmuScene();
-    e->host.parse(ss.str());
-    e->host.init();
+    e->host.dialect = dialect;
+    try {
+        e->host.parse(text);
+        e->host.init();
+    } catch (const std::exception&) {
+        delete e;
+        return nullptr;
+    }
     const FlatScene& F = e->host.flat;
     DevScene& S = e->dev;
     memset(&S, 0, sizeof S);
@@ -61,6 +63,27 @@ void* emu_scene_load(const char* path) {
     S.plights = (const float4*)F.plights.data();
     fill_dev_scalars(e->host, S);
     return e;
+}
+void* emu_scene_load(const char* path) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return nullptr;
+    std::ostringstream ss;
+    ss << in.rdbuf();
+    return emu_build(ss.str(), DIALECT_HW5);
+}
+void* emu_scene_parse_dialect(const char* text, long len, int dialect) { return emu_build(std::string(text, (size_t)len), dialect); }
+// the deterministic dialects (course_device.cuh): the whole frame as linear colours, (H, W, 3) floats
+int emu_frame_linear(void* h, float* out) {
+    EmuScene* e = (EmuScene*)h;
+    const DevScene& S = e->dev;
+    if (S.dialect != DIALECT_HW1 && S.dialect != DIALECT_HW2) return -1;
+    const long npix = (long)S.width * S.height;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < npix; ++i) {
+        vec3 c = S.dialect == DIALECT_HW1 ? raycast_pixel_hw1(S, (uint32_t)i) : whitted_pixel_hw2(S, (uint32_t)i);
+        out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+    }
+    return 0;
 }
 void emu_scene_free(void* h) { delete (EmuScene*)h; }
 
@@ -102,5 +125,40 @@ void emu_mix_sample(void* h, long n, const float* x, const float* nr, uint32_t s
         vec3 r = mix_sample(e->dev, g, mk3(x[3 * i], x[3 * i + 1], x[3 * i + 2]), mk3(nr[3 * i], nr[3 * i + 1], nr[3 * i + 2]));
         dir[3 * i] = r.x; dir[3 * i + 1] = r.y; dir[3 * i + 2] = r.z;
     }
+}
+
+// ---- the feature-specialised instantiations k_shade uses (FEAT = 0, FE_SPECULAR, FE_ALL): same results on a
+//      scene whose features they cover
+uint32_t emu_scene_features(void* h) { return ((EmuScene*)h)->dev.features; }
+}  // extern "C"
+template <uint32_t FEAT>
+static void shade_parts(const DevScene& S, long n, const float* x, const float* nr, uint32_t seed, float* dir, float* pdf,
+                        const int32_t* prim, const float* o, const float* d, float* tn) {
+    for (long i = 0; i < n; ++i) {
+        Rng g{seed, (uint32_t)i, 3u, 1u};
+        vec3 X = mk3(x[3 * i], x[3 * i + 1], x[3 * i + 2]), Nn = mk3(nr[3 * i], nr[3 * i + 1], nr[3 * i + 2]);
+        vec3 r = mix_sample<FEAT>(S, g, X, Nn);
+        dir[3 * i] = r.x; dir[3 * i + 1] = r.y; dir[3 * i + 2] = r.z;
+        pdf[i] = mix_pdf<FEAT>(S, X, Nn, r);
+        Isect is;
+        is.t = -1.f; is.n = mk3(0, 0, 0); is.interior = 0;
+        bool ok = prim[i] >= 0 && prim_intersect<false, FEAT>(S, (uint32_t)prim[i], mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]),
+                                                               mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), is);
+        tn[4 * i] = ok ? is.t : -1.f; tn[4 * i + 1] = is.n.x; tn[4 * i + 2] = is.n.y; tn[4 * i + 3] = is.n.z;
+        float cd; int id;
+        closest_plane<FEAT>(S, X, r, cd, id);
+        tn[4 * i] += 0.f * cd;  // keep the call alive without changing the output layout
+        pdf[i] = id >= 0 ? pdf[i] : -pdf[i];
+    }
+}
+extern "C" {
+int emu_shade_parts(void* h, uint32_t feat, long n, const float* x, const float* nr, uint32_t seed, float* dir, float* pdf,
+                    const int32_t* prim, const float* o, const float* d, float* tn) {
+    const DevScene& S = ((EmuScene*)h)->dev;
+    if (feat == 0) shade_parts<0>(S, n, x, nr, seed, dir, pdf, prim, o, d, tn);
+    else if (feat == FE_SPECULAR) shade_parts<FE_SPECULAR>(S, n, x, nr, seed, dir, pdf, prim, o, d, tn);
+    else if (feat == FE_ALL) shade_parts<FE_ALL>(S, n, x, nr, seed, dir, pdf, prim, o, d, tn);
+    else return -1;
+    return 0;
 }
 }

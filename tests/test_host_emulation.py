@@ -19,7 +19,8 @@ CSRC = os.path.join(ROOT, "raytracing-course_b200", "csrc")
 @pytest.fixture(scope="module")
 def emu():
     so = os.path.join(EMU_DIR, "libemul.so")
-    srcs = [os.path.join(EMU_DIR, "emul.cpp"), os.path.join(CSRC, "rt_device.cuh"), os.path.join(CSRC, "bvh_build.cpp")]
+    srcs = [os.path.join(EMU_DIR, "emul.cpp"), os.path.join(CSRC, "rt_device.cuh"), os.path.join(CSRC, "course_device.cuh"),
+            os.path.join(CSRC, "device_scene.h"), os.path.join(CSRC, "bvh_build.cpp")]
     objs = [os.path.join(CSRC, "build", "scene_load.o"), os.path.join(CSRC, "build", "bvh_build.o")]
     if not all(os.path.exists(o) for o in objs):
         pytest.skip("product objects not built")
@@ -34,6 +35,12 @@ def emu():
     L.emu_scene_load.restype = C.c_void_p
     L.emu_scene_load.argtypes = [C.c_char_p]
     L.emu_scene_free.argtypes = [C.c_void_p]
+    L.emu_scene_parse_dialect.restype = C.c_void_p
+    L.emu_scene_parse_dialect.argtypes = [C.c_char_p, C.c_long, C.c_int]
+    L.emu_frame_linear.argtypes = [C.c_void_p, f32p]
+    L.emu_scene_features.restype = C.c_uint32
+    L.emu_scene_features.argtypes = [C.c_void_p]
+    L.emu_shade_parts.argtypes = [C.c_void_p, C.c_uint32, C.c_long, f32p, f32p, C.c_uint32, f32p, f32p, i32p, f32p, f32p, f32p]
     L.emu_intersect.argtypes = [C.c_void_p, C.c_long, f32p, f32p, C.c_int, i32p, f32p, f32p, i32p, u64p]
     L.emu_mix_pdf.argtypes = [C.c_void_p, C.c_long, f32p, f32p, f32p, f32p]
     L.emu_mix_sample.argtypes = [C.c_void_p, C.c_long, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p]
@@ -111,4 +118,67 @@ def test_mix_pdf_and_sample(emu, oracle_scenes, name):
     # validity test is borderline may take one more turn of the rejection loop (1 in ~6000)
     err = np.abs(dirs - want).max(axis=1)
     assert (err <= 2e-5).mean() >= 0.999
+    emu.emu_scene_free(h)
+
+
+@pytest.mark.parametrize("fixture", ["hw1_course_sample6", "hw2_hw2_lights"])
+def test_deterministic_dialects_match_reference_images(emu, oracle_lib, fixture):
+    """csrc/course_device.cuh (hw1 ray casting, hw2 Whitted) compiled for the host against the image the
+    UNMODIFIED hwN program wrote for the same scene text (tests/golden/hwN_*.npz)."""
+    g = golden(fixture)
+    text = bytes(g["text"])
+    dialect = int(g["dialect"])
+    h = emu.emu_scene_parse_dialect(text, len(text), dialect)
+    assert h
+    want = g["u8"]
+    lin = np.zeros(want.shape, np.float32)
+    assert emu.emu_frame_linear(h, lin) == 0
+    emu.emu_scene_free(h)
+    got = np.zeros(want.size, np.uint8)
+    flat = np.ascontiguousarray(lin.reshape(-1, 3))
+    if dialect == 1:
+        oracle_lib.lib.orc_flat_u8(flat.shape[0], flat, got)
+    else:
+        oracle_lib.lib.orc_tonemap_u8(flat.shape[0], flat, got)
+    diff = np.abs(got.reshape(want.shape).astype(int) - want.astype(int))
+    # hw1 writes scene colours as they are: exact.  hw2: float summation order of the recursion may move
+    # a value across a rounding boundary (1 LSB, a handful of values).
+    if dialect == 1:
+        assert diff.max() == 0
+    else:
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("name,features", [("practice5_dragon_10k", 0), ("practice5_1", None), ("practice5_2", None), ("lights_mix", 7)])
+def test_feature_specialised_shading_is_bit_identical(emu, name, features):
+    """k_shade is compiled per scene-feature set (rotation / ellipsoid / specular); the host launches the smallest
+    instantiation covering DevScene::features.  On a scene it covers, a specialised instantiation must return
+    exactly what the full one does: light sampling, mix pdf, the winner's re-intersection, the plane loop."""
+    g = golden(name + "_rays")
+    h = emu.emu_scene_load(scene_path(name).encode())
+    have = emu.emu_scene_features(h)
+    if features is not None:
+        assert have == features
+    x = np.ascontiguousarray(g["sec_o"], np.float32)
+    n = len(x)
+    rng = np.random.default_rng(5)
+    nr = rng.normal(size=(n, 3)).astype(np.float32)
+    nr /= np.linalg.norm(nr, axis=1, keepdims=True)
+    o, d, prim = np.ascontiguousarray(g["cam_o"][:n], np.float32), np.ascontiguousarray(g["cam_d"][:n], np.float32), None
+    pid = emu_intersect(emu, h, o, d, 0)[0]
+    m = min(n, len(pid))
+    x, nr, o, d, pid = x[:m], nr[:m], o[:m], d[:m], np.ascontiguousarray(pid[:m], np.int32)
+
+    def run(feat):
+        dirs = np.zeros((m, 3), np.float32); pdf = np.zeros(m, np.float32); tn = np.zeros((m, 4), np.float32)
+        assert emu.emu_shade_parts(h, feat, m, x, nr, 77, dirs, pdf, pid, o, d, tn) == 0
+        return dirs, pdf, tn
+
+    full = run(7)
+    for feat in (0, 4):
+        if have & ~feat:
+            continue  # this instantiation does not cover the scene
+        part = run(feat)
+        for a, b in zip(full, part):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, feat)
     emu.emu_scene_free(h)

@@ -120,17 +120,42 @@ def render_fixture(name, width, height, samples, ray_depth=-1):
 def dialect_fixture(dialect, name, width=None, height=None, samples=None):
     """Image written by the unmodified hwN program (oracle/_ref/raytracing_hwN, built by oracle/Makefile from
     /root/reference/hwN) for scenes/<name>.txt with the header lines replaced; the fixture keeps the exact scene
-    text next to the 8-bit image, so a checker needs neither the scene file nor the reference."""
+    text next to the 8-bit image, so a checker needs neither the scene file nor the reference.  Monte Carlo
+    snapshots (hw3, hw4) also keep `u8_b`, the image of the same program at SAMPLES - 1: the programs seed their
+    generator with a constant, so this is the only way to see the reference's own noise level (which is NOT ours
+    when a scene has no EMISSION lines: `Color() = default` leaves Primitive::emission indeterminate in the
+    reference, hw4 src/scene.cpp:39-60 then lists such primitives as lights and samples towards them)."""
     import subprocess
     import tempfile
-    text = orclib.with_header(open(os.path.join(SCENES, name + ".txt")).read(), width, height, samples)
-    with tempfile.TemporaryDirectory() as td:
-        sp, op = os.path.join(td, "scene.txt"), os.path.join(td, "out.ppm")
-        open(sp, "w").write(text)
-        subprocess.run([orclib.ref_dialect_bin(dialect), sp, op], check=True, stderr=subprocess.DEVNULL)
-        img = orclib.read_ppm(op).copy()
+    base = open(os.path.join(SCENES, name + ".txt")).read()
+    text = orclib.with_header(base, width, height, samples)
+
+    def run(scene_text):
+        with tempfile.TemporaryDirectory() as td:
+            sp, op = os.path.join(td, "scene.txt"), os.path.join(td, "out.ppm")
+            open(sp, "w").write(scene_text)
+            subprocess.run([orclib.ref_dialect_bin(dialect), sp, op], check=True, stderr=subprocess.DEVNULL)
+            return orclib.read_ppm(op).copy()
+
+    img = run(text)
+    extra = {}
+    if dialect >= 3:
+        mirrored = []
+        for line in text.splitlines():
+            w = line.split()
+            if w and w[0] == "CAMERA_RIGHT":
+                line = "CAMERA_RIGHT " + " ".join(repr(-float(v)) for v in w[1:4])
+            mirrored.append(line)
+        second = run("\n".join(mirrored) + "\n")[:, ::-1].copy()
+        if dialect == 3:
+            # hw3's Camera::GetToRay(float, float) adds half a pixel (hw3 src/scene.cpp:186-187): its samples cover
+            # [x + 0.5, x + 1.5), so the mirrored frame flipped back is one column to the right of the plain one.
+            # Column x of the plain frame pairs with column x + 1 here; the last column has no partner and
+            # repeats the plain frame (its noise estimate is 0: one column of the frame).
+            second = np.concatenate([second[:, 1:], img[:, -1:]], axis=1)
+        extra["u8_b"] = second
     out = "hw%d_%s.npz" % (dialect, name)
-    np.savez_compressed(os.path.join(GOLD, out), u8=img, text=np.frombuffer(text.encode(), np.uint8), dialect=dialect)
+    np.savez_compressed(os.path.join(GOLD, out), u8=img, text=np.frombuffer(text.encode(), np.uint8), dialect=dialect, **extra)
     print(out, img.shape, "mean", img.mean(axis=(0, 1)).round(2))
 
 

@@ -301,10 +301,11 @@ def main():
         visits_per_ray = stats["index_node_visits"] / max(stats["traversed_rays"], 1)
         tests_per_ray = stats["prim_tests"] / max(stats["traversed_rays"], 1)
         planes = scene.nprims - scene.nbvh
+        node_bytes = scene.stats().get("index_node_bytes", 64)   # 96: child boxes + child cones + refs
         alg = {  # (bytes per unit, units processed in the timed region, kernel)
-            "traverse": (4 + 32 + 4 + 4 + 64 * visits_per_ray + 48 * tests_per_ray, trav0,
+            "traverse": (4 + 32 + 4 + 4 + node_bytes * visits_per_ray + 48 * tests_per_ray, trav0,
                          "k_traverse" if args.traversal == 0 else "k_extend_reftree"),
-            "pre": (32 + 8 + 64 + 32 * planes + 4 * (trav0 / rays0), rays0, "k_pre"),
+            "pre": (32 + 8 + node_bytes + 32 * planes + 4 * (trav0 / rays0), rays0, "k_pre"),
             "shade": (64 + 4 + 48 + 32 + 64 + 12, rays0, "k_shade"),
         }
         top = max(alg, key=lambda k: prof[k]["ms"])

@@ -65,7 +65,7 @@ int rtc_scene_upload(rtc_scene* s, uint64_t* h2d_bytes);
 /* out: width,height,ray_depth,samples,nprims,nbvh(non-plane prims),nnodes(reference BVH),nlights */
 int rtc_scene_info(const rtc_scene* s, uint32_t out[8]);
 /* out: index-BVH nodes, index-BVH depth, reference-BVH depth, units(reference leaves),
- *      device bytes of the scene, LCA table levels, 0, 0 */
+ *      device bytes of the scene, LCA table levels, bytes per index node, scene feature bits */
 int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]);
 /* DIMENSIONS / SAMPLES / RAY_DEPTH overrides (value < 0 keeps the file's) */
 int rtc_scene_override(rtc_scene* s, int width, int height, int samples, int ray_depth);

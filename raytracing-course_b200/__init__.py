@@ -203,8 +203,8 @@ class Scene:
     def stats(self):
         out = np.zeros(8, np.uint64)
         _check(self.lib, self.lib.rtc_scene_stats(self.h, out))
-        keys = ["index_nodes", "index_depth", "ref_depth", "units", "device_bytes", "lca_levels"]
-        return dict(zip(keys, [int(v) for v in out[:6]]))
+        keys = ["index_nodes", "index_depth", "ref_depth", "units", "device_bytes", "lca_levels", "index_node_bytes", "features"]
+        return dict(zip(keys, [int(v) for v in out[:8]]))
 
     def override(self, width=-1, height=-1, samples=-1, ray_depth=-1):
         _check(self.lib, self.lib.rtc_scene_override(self.h, width, height, samples, ray_depth))

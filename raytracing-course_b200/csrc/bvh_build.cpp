@@ -126,11 +126,78 @@ struct RefBuilder {
 // Index BVH: a SAH tree over the reference's LEAVES ("units"), built binary and collapsed to 4-wide nodes.  Every unit keeps
 // exactly the AABB the reference stores for that leaf; traversal reports all units whose AABB
 // the ray touches (no ordering, no early out -- see the header comment).
+// Feasibility cone of a set of reference leaves: every ray that can produce a hit in the set has its direction
+// within `alpha` of +axis or of -axis.  Why such a cone exists: Primitive::IntersectTriangle intersects the plane
+// through the ORIGIN (src/primitives.cpp:155-157), so triangle T = (a, b, c) with unit normal n is rendered as
+// T' = T - (a.n) n, while BVH_t::Intersect_ still demands that the ray touches the AABB of the real T
+// (src/bvh.cpp:194-198).  A ray through a point of T' and a point x of a box that contains T has direction
+// (a.n) n + (x - q), q in T: within asin(diag(box) / |a.n|) of +-n.  alpha >= pi/2 means "no restriction".
+struct Cone {
+    double ax = 0, ay = 0, az = 1, alpha = 4.0;
+    bool open() const { return !(alpha < 1.5707); }
+};
+static Cone merge_cones(const Cone& a, const Cone& b) {
+    if (a.open() || b.open()) return Cone{};
+    double dt = a.ax * b.ax + a.ay * b.ay + a.az * b.az;
+    const double sgn = dt < 0 ? -1.0 : 1.0;  // +-axis describe the same double cone: take the closer one
+    dt = std::min(1.0, std::fabs(dt));
+    const double bx = sgn * b.ax, by = sgn * b.ay, bz = sgn * b.az;
+    const double gamma = std::acos(dt);
+    if (gamma + b.alpha <= a.alpha) return a;
+    if (gamma + a.alpha <= b.alpha) return Cone{bx, by, bz, b.alpha};
+    Cone r;
+    r.alpha = 0.5 * (gamma + a.alpha + b.alpha) * (1.0 + 1e-9) + 1e-9;
+    if (r.open()) return Cone{};
+    // axis: a's axis turned towards b's by (alpha_new - a.alpha), inside the plane of the two (slerp)
+    const double tt = (r.alpha - a.alpha) / gamma;
+    const double sg = std::sin(gamma);
+    const double wa = std::sin((1.0 - tt) * gamma) / sg, wb = std::sin(tt * gamma) / sg;
+    r.ax = wa * a.ax + wb * bx; r.ay = wa * a.ay + wb * by; r.az = wa * a.az + wb * bz;
+    const double len = std::sqrt(r.ax * r.ax + r.ay * r.ay + r.az * r.az);
+    r.ax /= len; r.ay /= len; r.az /= len;
+    return r;
+}
+// cone of one reference leaf holding prims[first .. first + count) inside `box`
+static Cone cone_of_leaf(const std::vector<Primitive>& prims, uint32_t first, uint32_t count, const Aabb& box) {
+    const double ex = (double)box.mx.x - box.mn.x, ey = (double)box.mx.y - box.mn.y, ez = (double)box.mx.z - box.mn.z;
+    double scale = 0;
+    for (float v : {box.mn.x, box.mn.y, box.mn.z, box.mx.x, box.mx.y, box.mx.z}) scale = std::max(scale, (double)std::fabs(v));
+    // generous slack for the float arithmetic of the slab test and of the orientation tests
+    const double diag = std::sqrt(ex * ex + ey * ey + ez * ez) * 1.001 + 1e-5 * scale + 1e-30;
+    if (!(diag < 1e30)) return Cone{};
+    Cone all;
+    bool have = false;
+    for (uint32_t i = first; i < first + count; ++i) {
+        const Primitive& p = prims[i];
+        const bool ident = p.rot.x == 0.f && p.rot.y == 0.f && p.rot.z == 0.f && p.rot.w == 1.f && p.pos.x == 0.f &&
+                           p.pos.y == 0.f && p.pos.z == 0.f;
+        if (p.type != PT_TRIANGLE || !ident) return Cone{};
+        const double ux = (double)p.d1.x - p.d0.x, uy = (double)p.d1.y - p.d0.y, uz = (double)p.d1.z - p.d0.z;
+        const double vx = (double)p.d2.x - p.d0.x, vy = (double)p.d2.y - p.d0.y, vz = (double)p.d2.z - p.d0.z;
+        double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+        const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+        if (!(len > 1e-30)) return Cone{};  // degenerate triangle: its float normal is noise
+        nx /= len; ny /= len; nz /= len;
+        const double h = std::fabs(p.d0.x * nx + p.d0.y * ny + p.d0.z * nz);
+        // the device tests with the FLOAT normal (normalize(cross) in float, relative error ~1e-6 per
+        // component, far more for slivers): its plane offset and direction differ from ours by that much
+        const double sliver = 4e-7 * (std::sqrt(ux * ux + uy * uy + uz * uz) * std::sqrt(vx * vx + vy * vy + vz * vz)) / len;
+        const double ratio = (diag + sliver * (h + scale)) / h;
+        if (!(ratio < 0.999)) return Cone{};
+        Cone c{nx, ny, nz, std::asin(ratio) + sliver};
+        all = have ? merge_cones(all, c) : c;
+        have = true;
+        if (all.open()) return Cone{};
+    }
+    return have ? all : Cone{};
+}
+
 struct Unit {
     Aabb box;
     uint32_t first, count;
     vec3 centre;
     bool fast;  // a single untransformed triangle: its box is min/max of its vertices
+    Cone cone;
 };
 // float -> IEEE half bits, round to nearest even (finite inputs; overflow gives infinity)
 static uint16_t half_bits_rn(float f) {
@@ -191,10 +258,10 @@ struct IndexBuilder {
         for (uint32_t i = lo; i < hi; ++i) grow(b, units[order[i]].box);
         return b;
     }
-    // returns the child reference for units order[lo..hi)
-    uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth) {
+    // returns the child reference for units order[lo..hi) and the feasibility cone of that subtree
+    uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth, Cone& cone) {
         max_depth = std::max(max_depth, depth);
-        if (hi - lo == 1) return leaf_ref(units[order[lo]]);
+        if (hi - lo == 1) { cone = units[order[lo]].cone; return leaf_ref(units[order[lo]]); }
         float best = 3.0e38f;
         int best_axis = -1;
         uint32_t best_cut = 0;
@@ -225,15 +292,18 @@ struct IndexBuilder {
         uint32_t me = (uint32_t)tmp.size();
         tmp.push_back(Bin{});
         Aabb lb = bound(lo, best_cut), rb = bound(best_cut, hi);
-        uint32_t lref = build(lo, best_cut, depth + 1);
-        uint32_t rref = build(best_cut, hi, depth + 1);
-        tmp[me] = Bin{{lb, rb}, {lref, rref}};
+        Cone lc, rc;
+        uint32_t lref = build(lo, best_cut, depth + 1, lc);
+        uint32_t rref = build(best_cut, hi, depth + 1, rc);
+        tmp[me] = Bin{{lb, rb}, {lref, rref}, {lc, rc}};
+        cone = merge_cones(lc, rc);
         return me;
     }
 
     struct Bin {
         Aabb box[2];
         uint32_t ref[2];
+        Cone cone[2];
     };
     std::vector<Bin> tmp;
     uint32_t wide_depth = 0;
@@ -243,8 +313,8 @@ struct IndexBuilder {
     // slots are filled.  Returns the index of the emitted node.
     uint32_t emit(uint32_t b, uint32_t depth) {
         wide_depth = std::max(wide_depth, depth);
-        struct Slot { Aabb box; uint32_t ref; };
-        std::vector<Slot> slots = {{tmp[b].box[0], tmp[b].ref[0]}, {tmp[b].box[1], tmp[b].ref[1]}};
+        struct Slot { Aabb box; uint32_t ref; Cone cone; };
+        std::vector<Slot> slots = {{tmp[b].box[0], tmp[b].ref[0], tmp[b].cone[0]}, {tmp[b].box[1], tmp[b].ref[1], tmp[b].cone[1]}};
         while (slots.size() < 4) {
             int pick = -1;
             float area = -1.f;
@@ -252,12 +322,13 @@ struct IndexBuilder {
                 if (!(slots[i].ref & IREF_LEAF) && surface(slots[i].box) > area) { area = surface(slots[i].box); pick = (int)i; }
             if (pick < 0) break;
             const Bin& c = tmp[slots[pick].ref];
-            slots[pick] = Slot{c.box[0], c.ref[0]};
-            slots.push_back(Slot{c.box[1], c.ref[1]});
+            slots[pick] = Slot{c.box[0], c.ref[0], c.cone[0]};
+            slots.push_back(Slot{c.box[1], c.ref[1], c.cone[1]});
         }
-        uint32_t me = (uint32_t)(out.size() / 4);
-        out.resize(out.size() + 4, f4{0, 0, 0, 0});
+        uint32_t me = (uint32_t)(out.size() / kIndexNodeF4);
+        out.resize(out.size() + kIndexNodeF4, f4{0, 0, 0, 0});
         uint16_t hv[6][4];
+        uint16_t cv[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // axis x, y, z, threshold; all 0 = never culled
         uint32_t refs[4];
         for (int i = 0; i < 4; ++i) {
             bool used = i < (int)slots.size();
@@ -280,6 +351,19 @@ struct IndexBuilder {
             hv[0][i] = half_down(bx.mn.x); hv[1][i] = half_down(bx.mn.y); hv[2][i] = half_down(bx.mn.z);
             hv[3][i] = half_up(bx.mx.x); hv[4][i] = half_up(bx.mx.y); hv[5][i] = half_up(bx.mx.z);
 #endif
+            if (used && !slots[i].cone.open()) {
+                // The device culls the child when |dn . axis| < threshold, dn = normalised ray direction, all in
+                // half precision: the axis components round to nearest (error <= 8.7e-4 in the dot product), dn
+                // likewise, three half products / sums add <= 2.5e-3; the threshold gives 8e-3 away and is
+                // rounded down.  A threshold that ends up <= 0 leaves the child unrestricted.
+                const Cone& c = slots[i].cone;
+                const double thr = std::cos(std::min(c.alpha + 2e-3, 1.5707963)) - 8e-3;
+                if (thr > 0) {
+                    cv[0][i] = half_bits_rn((float)c.ax); cv[1][i] = half_bits_rn((float)c.ay); cv[2][i] = half_bits_rn((float)c.az);
+                    cv[3][i] = half_down((float)thr);
+                    if (cv[3][i] & 0x8000u) cv[3][i] = 0;
+                }
+            }
             refs[i] = IREF_NONE;
             if (used) refs[i] = (slots[i].ref & IREF_LEAF) ? slots[i].ref : emit(slots[i].ref, depth + 1);
         }
@@ -289,7 +373,17 @@ struct IndexBuilder {
             w[2 * r + 1] = (uint32_t)hv[r][2] | ((uint32_t)hv[r][3] << 16);
         }
         for (int i = 0; i < 4; ++i) w[12 + i] = refs[i];
-        for (int q = 0; q < 4; ++q) out[4 * me + q] = bits4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) out[kIndexNodeF4 * me + q] = bits4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+#if RTC_NODE_CONES
+        // q4 = axis.x[0..3] axis.y[0..3] ; q5 = axis.z[0..3] threshold[0..3]  (halves, two children per word)
+        uint32_t cw[8];
+        for (int r = 0; r < 4; ++r) {
+            cw[2 * r] = (uint32_t)cv[r][0] | ((uint32_t)cv[r][1] << 16);
+            cw[2 * r + 1] = (uint32_t)cv[r][2] | ((uint32_t)cv[r][3] << 16);
+        }
+        out[kIndexNodeF4 * me + 4] = bits4(cw[0], cw[1], cw[2], cw[3]);
+        out[kIndexNodeF4 * me + 5] = bits4(cw[4], cw[5], cw[6], cw[7]);
+#endif
         return me;
     }
 };
@@ -404,7 +498,8 @@ void HostScene::init() {
                     bool ident = p0.rot.x == 0.f && p0.rot.y == 0.f && p0.rot.z == 0.f && p0.rot.w == 1.f &&
                                  p0.pos.x == 0.f && p0.pos.y == 0.f && p0.pos.z == 0.f;
                     bool fast = nd.count == 1 && p0.type == PT_TRIANGLE && ident;
-                    units.push_back(Unit{nd.box, nd.first, nd.count, 0.5f * (nd.box.mx + nd.box.mn), fast});
+                    units.push_back(Unit{nd.box, nd.first, nd.count, 0.5f * (nd.box.mx + nd.box.mn), fast,
+                                         cone_of_leaf(prims, nd.first, nd.count, nd.box)});
                 }
             } else {
                 F.rmeta[v] = u4{nd.first, nodes[nd.right].first, depth[v], 0};
@@ -429,7 +524,8 @@ void HostScene::init() {
         IndexBuilder ib{units, {}, F.inodes, std::vector<float>(units.size() + 1, 0.f)};
         ib.order.resize(units.size());
         std::iota(ib.order.begin(), ib.order.end(), 0u);
-        uint32_t broot = ib.build(0, (uint32_t)units.size(), 0);
+        Cone whole;
+        uint32_t broot = ib.build(0, (uint32_t)units.size(), 0, whole);
         F.iroot = (broot & IREF_LEAF) ? broot : ib.emit(broot, 1);
         F.index_depth = ib.wide_depth;
     }

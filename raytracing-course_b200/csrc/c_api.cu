@@ -368,8 +368,8 @@ int rtc_scene_info(const rtc_scene* s, uint32_t out[8]) {
 int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]) {
     if (!s || !out) return fail(RTC_ERR_ARG, "null argument");
     const FlatScene& F = s->host.flat;
-    out[0] = F.inodes.size() / 4; out[1] = F.index_depth; out[2] = F.ref_depth; out[3] = F.units;
-    out[4] = s->device_bytes; out[5] = F.lca_levels; out[6] = 0; out[7] = 0;
+    out[0] = F.inodes.size() / kIndexNodeF4; out[1] = F.index_depth; out[2] = F.ref_depth; out[3] = F.units;
+    out[4] = s->device_bytes; out[5] = F.lca_levels; out[6] = kIndexNodeF4 * sizeof(f4); out[7] = F.features;
     return RTC_OK;
 }
 int rtc_scene_override(rtc_scene* s, int width, int height, int samples, int ray_depth) {

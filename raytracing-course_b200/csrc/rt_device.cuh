@@ -452,8 +452,49 @@ RT_D void slab_ch(float cx, float cy, float cz, float hx, float hy, float hz, ve
     hit = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
 }
 #endif
-RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) {
-    const float4* nd = S.inodes + 4 * (size_t)node;
+// Feasibility cones (bvh_build.cpp Cone): the normalised ray direction as halves, (x, y) and (z, z).
+struct ConeDir {
+    uint32_t xy, zz;
+};
+RT_D uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+RT_D ConeDir cone_dir(vec3 d) {
+    // scale by the largest component first: |d|^2 must neither overflow nor vanish
+    float m = fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fabsf(d.z));
+    vec3 e = d * (1.f / m);
+    float k = 1.f / sqrtf(dot(e, e));
+    ConeDir c;
+    c.xy = pack_half2(e.x * k, e.y * k);
+    c.zz = pack_half2(e.z * k, e.z * k);
+    return c;  // a zero or non-finite direction gives NaN halves: every comparison below is then false = not culled
+}
+// children (2j, 2j + 1) of a node: bit 0 / bit 16 set when the child cannot be hit by a ray of this direction,
+// |dn . axis| < threshold in half arithmetic (the thresholds carry the rounding slack, bvh_build.cpp emit)
+RT_D uint32_t cone_cull_pair(ConeDir dn, float wx, float wy, float wz, float wt) {
+#ifdef __CUDA_ARCH__
+    const __half2 xy = *reinterpret_cast<const __half2*>(&dn.xy), zz = *reinterpret_cast<const __half2*>(&dn.zz);
+    const uint32_t ux = __float_as_uint(wx), uy = __float_as_uint(wy), uz = __float_as_uint(wz), ut = __float_as_uint(wt);
+    const __half2 ax = *reinterpret_cast<const __half2*>(&ux), ay = *reinterpret_cast<const __half2*>(&uy);
+    const __half2 az = *reinterpret_cast<const __half2*>(&uz), th = *reinterpret_cast<const __half2*>(&ut);
+    __half2 dt = __hmul2(ax, __low2half2(xy));
+    dt = __hfma2(ay, __high2half2(xy), dt);
+    dt = __hfma2(az, zz, dt);
+    return __hlt2_mask(__habs2(dt), th) & 0x00010001u;
+#else
+    // host compilation (tests/host_emul): the same operations, each rounded to half
+    auto h = [](float f) { return __half2float(__float2half_rn(f)); };
+    const float2 d_xy = unpack_half2(__uint_as_float(dn.xy)), d_zz = unpack_half2(__uint_as_float(dn.zz));
+    const float2 ax = unpack_half2(wx), ay = unpack_half2(wy), az = unpack_half2(wz), th = unpack_half2(wt);
+    float d0 = h(ax.x * d_xy.x), d1 = h(ax.y * d_xy.x);
+    d0 = h(fmaf(ay.x, d_xy.y, d0)); d1 = h(fmaf(ay.y, d_xy.y, d1));
+    d0 = h(fmaf(az.x, d_zz.x, d0)); d1 = h(fmaf(az.y, d_zz.x, d1));
+    return (fabsf(d0) < th.x ? 1u : 0u) | (fabsf(d1) < th.y ? 0x10000u : 0u);
+#endif
+}
+RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi, ConeDir dn) {
+    const float4* nd = S.inodes + kIndexNodeF4 * (size_t)node;
     float4 q0, q1, q2, q3;
     ldg8(nd, q0, q1);
     ldg8(nd + 2, q2, q3);
@@ -476,6 +517,15 @@ RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi) 
     slab(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, v.ref[1], v.hit[1], tc);
     slab(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, v.ref[2], v.hit[2], tc);
     slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, v.ref[3], v.hit[3], tc);
+#endif
+#if RTC_NODE_CONES
+    float4 q4, q5;
+    ldg8(nd + 4, q4, q5);  // axis.x[0..3] axis.y[0..3] | axis.z[0..3] threshold[0..3]
+    const uint32_t c01 = cone_cull_pair(dn, q4.x, q4.z, q5.x, q5.z), c23 = cone_cull_pair(dn, q4.y, q4.w, q5.y, q5.w);
+    v.hit[0] = v.hit[0] && !(c01 & 1u); v.hit[1] = v.hit[1] && !(c01 >> 16);
+    v.hit[2] = v.hit[2] && !(c23 & 1u); v.hit[3] = v.hit[3] && !(c23 >> 16);
+#else
+    (void)dn;
 #endif
     return v;
 }
@@ -528,6 +578,7 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
     if (S.iroot == IREF_NONE) return true;
     vec3 inv = ray_inv(d);
     vec3 oi = o * inv;
+    const ConeDir dn = cone_dir(d);
     uint32_t stack[kIndexStack];
     int sp = 0;
     uint32_t ref = S.iroot;
@@ -544,7 +595,7 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
             continue;
         }
         if (visits) ++*visits;
-        NodeVisit v = index_visit(S, ref, inv, oi);
+        NodeVisit v = index_visit(S, ref, inv, oi, dn);
         bool have = false;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {

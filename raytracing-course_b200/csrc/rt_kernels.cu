@@ -18,6 +18,18 @@ namespace rtc {
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = 32;           // queue slots a warp reserves per atomic
 
+// Wavefront state (paths, hits, queues) is written once and read once per bounce: 1.4 GB per k_shade launch
+// streams through a 126 MB L2 that should keep the 34 MB of BVH nodes and triangles k_traverse gathers from.
+// Every state access is marked evict-first (ld.global.cs / st.global.cs; +0.5 % measured, RTC_NO_STREAM_STATE
+// restores plain accesses for A/B runs).
+#ifndef RTC_NO_STREAM_STATE
+#define WF_LD(ptr) __ldcs(ptr)
+#define WF_ST(ptr, v) __stcs(ptr, v)
+#else
+#define WF_LD(ptr) (*(ptr))
+#define WF_ST(ptr, v) (*(ptr) = (v))
+#endif
+
 // Planes (src/scene.cpp:50-66) and the root of the index BVH for one fresh ray: cd = closest_dist
 // handed to BVH_t::Intersect, id = the plane hit so far; returns whether the ray touches any
 // child box of the index root (only those rays are queued for k_traverse).
@@ -32,7 +44,7 @@ RT_D bool pre_step(const DevScene& S, vec3 o, vec3 d, float& cd, uint32_t& id) {
         return ref_box(S, S.root, o, d, te, interior, l, r);
     }
     vec3 inv = ray_inv(d);
-    NodeVisit v = index_visit(S, S.iroot, inv, o * inv);
+    NodeVisit v = index_visit(S, S.iroot, inv, o * inv, cone_dir(d));
     return v.hit[0] || v.hit[1] || v.hit[2] || v.hit[3];
 }
 // warp-aggregated append of slot `i` to the traverse queue; call with the full warp converged
@@ -42,7 +54,7 @@ RT_D void enqueue(bool enters, uint32_t i, uint32_t* tq, uint32_t* tq_count, uin
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(tq_count, (uint32_t)__popc(mask));
         base = __shfl_sync(kFullMask, base, 0);
-        if (enters) tq[base + __popc(mask & ((1u << lane) - 1u))] = i;
+        if (enters) WF_ST(tq + base + __popc(mask & ((1u << lane) - 1u)), i);
     }
 }
 
@@ -69,14 +81,14 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, HitSoA 
             if (S.dialect == DIALECT_HW3) { fx = __fadd_rn(fx, 0.5f); fy = __fadd_rn(fy, 0.5f); }
             vec3 o, d;
             camera_ray(S, fx, fy, o, d);
-            P.o[i] = make_float4(o.x, o.y, o.z, 0.f);
-            P.d[i] = make_float4(d.x, d.y, d.z, 0.f);
-            P.beta[i] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
-            P.rad[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample));
+            WF_ST(P.o + i, make_float4(o.x, o.y, o.z, 0.f));
+            WF_ST(P.d + i, make_float4(d.x, d.y, d.z, 0.f));
+            WF_ST(P.beta + i, make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel)));
+            WF_ST(P.rad + i, make_float4(0.f, 0.f, 0.f, __uint_as_float(sample)));
             float cd; uint32_t id;
             enters = pre_step(S, o, d, cd, id);
-            H.cd[i] = cd;
-            H.id[i] = id;
+            WF_ST(H.cd + i, cd);
+            WF_ST(H.id + i, id);
         }
         enqueue(enters, i, tq, tq_count, lane);
     }
@@ -95,9 +107,9 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
         bool enters = false;
         if (i < count) {
             float cd; uint32_t id;
-            enters = pre_step(S, ld3(P.o[i]), ld3(P.d[i]), cd, id);
-            H.cd[i] = cd;
-            H.id[i] = id;
+            enters = pre_step(S, ld3(WF_LD(P.o + i)), ld3(WF_LD(P.d + i)), cd, id);
+            WF_ST(H.cd + i, cd);
+            WF_ST(H.id + i, id);
         }
         enqueue(enters, i, tq, tq_count, lane);
     }
@@ -119,7 +131,7 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 #define RTC_LEAF_FIRST 8
 #endif
 #ifndef RTC_VISIT_QUORUM
-#define RTC_VISIT_QUORUM 14   // sweep on B200: 10: 23.6, 12: 22.6, 14: 22.4, 16: 23.0, 20: 23.5 ms/step
+#define RTC_VISIT_QUORUM 16   // sweep on B200 with cone nodes: 10: 20.2, 12: 19.7, 14: 19.3, 16: 19.05 ms/step (64-byte nodes: 14 was best)
 #endif
 constexpr int kVisitQuorum = RTC_VISIT_QUORUM;
 #ifndef RTC_LAZY_OVERFLOW
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
     bool active = false, overflow = false;
     uint32_t ray = 0, node = kNone;
     vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), inv = mk3(0, 0, 0), oi = mk3(0, 0, 0);
+    ConeDir dn{0u, 0u};
     float cd0 = 0.f;
     int sp = 0, nl = 0, k = 0;
     uint32_t stk[kStackWords];
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
             // ---- VISIT: one inner node per ready lane; leaf children are only noted
             if (canV) {
                 if (STATS) ++visits;
-                NodeVisit v = index_visit(S, node, inv, oi);
+                NodeVisit v = index_visit(S, node, inv, oi, dn);
                 const int spm = sp > 0 ? sp - 1 : 0;
                 const uint32_t top = stk[spm];
                 uint32_t next = kNone;
@@ -220,7 +233,7 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
                 BestHit b;
                 if (overflow) { b = trace_reftree(S, o, d, cd0); ++fallbacks; }
                 else b = replay_reference(S, o, d, cd0, rec, k);
-                if (b.id != -1 && b.t < cd0) H.id[ray] = (uint32_t)b.id;  // src/scene.cpp:68-74
+                if (b.id != -1 && b.t < cd0) WF_ST(H.id + ray, (uint32_t)b.id);  // src/scene.cpp:68-74
                 active = false;
             }
         } else {
@@ -235,12 +248,13 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
             uint32_t rank = __popc(mR & lt_mask);
             uint32_t serve = min((uint32_t)nR, pool_left);
             if (canR && rank < serve) {
-                ray = __ldg(tq + pool_base + rank);
-                o = ld3(P.o[ray]);
-                d = ld3(P.d[ray]);
-                cd0 = H.cd[ray];
+                ray = WF_LD(tq + pool_base + rank);
+                o = ld3(WF_LD(P.o + ray));
+                d = ld3(WF_LD(P.d + ray));
+                cd0 = WF_LD(H.cd + ray);
                 inv = ray_inv(d);
                 oi = o * inv;
+                dn = cone_dir(d);
                 sp = 0; nl = 0; k = 0; overflow = false;
                 active = true;
                 if (S.iroot & IREF_LEAF) {  // single-leaf tree
@@ -264,14 +278,14 @@ __global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA 
 __global__ void __launch_bounds__(128) k_extend_reftree(DevScene S, PathSoA P, HitSoA H, const uint32_t* qcount) {
     const uint32_t count = *qcount;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
+        vec3 o = ld3(WF_LD(P.o + i)), d = ld3(WF_LD(P.d + i));
         float closest;
         int id;
         closest_plane(S, o, d, closest, id);
         BestHit b = trace_reftree(S, o, d, closest);
         if (b.id != -1 && b.t < closest) id = b.id;
-        H.cd[i] = closest;
-        H.id[i] = id < 0 ? HIT_MISS : (uint32_t)id;
+        WF_ST(H.cd + i, closest);
+        WF_ST(H.id + i, id < 0 ? HIT_MISS : (uint32_t)id);
     }
 }
 
@@ -286,15 +300,23 @@ RT_D void deposit(float* accum, uint32_t pixel, vec3 L) {
 // L = sum_k beta_k * E_k.  Surviving paths are written compacted (warp ballot + one atomic per
 // warp) into the next queue; finished paths add their radiance to the pixel sum.
 #ifndef RTC_SHADE_THREADS
-#define RTC_SHADE_THREADS 128   // 128 x 6 blocks/SM (80 registers, 76 B spills) measured best: profiles/r01_experiments.md
-#define RTC_SHADE_MIN_BLOCKS 6
+#define RTC_SHADE_THREADS 128
+#endif
+// blocks per SM: the full kernel runs best at 6 (80 registers, 40 B spilled); the instantiations without rotation and
+// ellipsoid code fit 64 registers without spilling and gain from 8 (shade 8.3 -> 7.5 ms; 9 / 10 / 12 blocks spill and
+// lose again): profiles/r01_experiments.md
+#ifndef RTC_SHADE_MIN_BLOCKS_FULL
+#define RTC_SHADE_MIN_BLOCKS_FULL 6
+#endif
+#ifndef RTC_SHADE_MIN_BLOCKS_LEAN
+#define RTC_SHADE_MIN_BLOCKS_LEAN 8
 #endif
 // HW3 = the hw3 snapshot's diffuse term (hw3 src/scene.cpp:238-249): a direction uniform on the hemisphere
 // around the normal, weight 2 C cos; every other line of the switch is common to hw3, hw4 and hw5.
 // FEAT = the scene features this instantiation supports (rt_device.cuh prim_flags_for): the kernel is bound by
 // instruction fetch, and the course's dragon scenes use a third of its code (no rotation, no ellipsoid, diffuse).
 template <bool HW3, uint32_t FEAT>
-__global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
+__global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_ELLIPSOID)) ? RTC_SHADE_MIN_BLOCKS_FULL : RTC_SHADE_MIN_BLOCKS_LEAN) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                                                 uint32_t* qout, uint32_t* tq, uint32_t* tq_count, float* accum, uint32_t bounce,
                                                 uint32_t seed) {
     const uint32_t count = *qin;
@@ -306,12 +328,12 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
         vec3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0), beta = mk3(0, 0, 0), L = mk3(0, 0, 0);
         uint32_t pixel = 0, sample = 0;
         if (i < count) {
-            float4 b4 = P.beta[i], r4 = P.rad[i];
+            float4 b4 = WF_LD(P.beta + i), r4 = WF_LD(P.rad + i);
             beta = ld3(b4); L = ld3(r4);
             pixel = __float_as_uint(b4.w); sample = __float_as_uint(r4.w);
-            uint32_t prim = H.id[i];
+            uint32_t prim = WF_LD(H.id + i);
             Isect is;
-            vec3 o = ld3(P.o[i]), d = ld3(P.d[i]);
+            vec3 o = ld3(WF_LD(P.o + i)), d = ld3(WF_LD(P.d + i));
             if (prim == HIT_MISS || !prim_intersect<false, FEAT>(S, prim, o, d, is)) {
                 L = L + beta * mk3(S.bg.x, S.bg.y, S.bg.z);  // src/scene.cpp:92-94
             } else {
@@ -392,15 +414,15 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, RTC_SHADE_MIN_BLOCKS) k_sha
             base = __shfl_sync(kFullMask, base, 0);
             if (alive) {
                 dst = base + __popc(mask & ((1u << lane) - 1u));
-                N.o[dst] = make_float4(no.x, no.y, no.z, 0.f);
-                N.d[dst] = make_float4(nd.x, nd.y, nd.z, 0.f);
-                N.beta[dst] = make_float4(beta.x, beta.y, beta.z, __uint_as_float(pixel));
-                N.rad[dst] = make_float4(L.x, L.y, L.z, __uint_as_float(sample));
+                WF_ST(N.o + dst, make_float4(no.x, no.y, no.z, 0.f));
+                WF_ST(N.d + dst, make_float4(nd.x, nd.y, nd.z, 0.f));
+                WF_ST(N.beta + dst, make_float4(beta.x, beta.y, beta.z, __uint_as_float(pixel)));
+                WF_ST(N.rad + dst, make_float4(L.x, L.y, L.z, __uint_as_float(sample)));
                 // first part of the next Scene::RayIntersection, while the ray is still in registers
                 float cd; uint32_t id;
                 enters = pre_step<FEAT>(S, no, nd, cd, id);
-                HN.cd[dst] = cd;
-                HN.id[dst] = id;
+                WF_ST(HN.cd + dst, cd);
+                WF_ST(HN.id + dst, id);
             }
             enqueue(enters, dst, tq, tq_count, lane);
         }

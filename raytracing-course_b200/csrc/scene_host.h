@@ -10,6 +10,11 @@
 // Index-BVH child boxes as fp16 (centre, half-extent) instead of (min, max): the slab test then
 // runs on the FMA pipe (3 FFMA per child and axis) instead of 2 FFMA + 2 FMNMX; k_traverse is bound
 // by the ALU pipe (profiles/r01_experiments.md).  0 selects the min/max layout for A/B runs.
+// Index nodes carry a direction cone per child (DESIGN.md "Feasibility cones"): 6 float4 = 96 bytes per node
+// instead of 4 float4 = 64 bytes.  RTC_NODE_CONES=0 builds the plain 64-byte nodes.
+#ifndef RTC_NODE_CONES
+#define RTC_NODE_CONES 1
+#endif
 #ifndef RTC_NODE_CENTRE_HALF
 #define RTC_NODE_CENTRE_HALF 1
 #endif
@@ -137,6 +142,7 @@ constexpr uint32_t IREF_NONE = 0xFFFFFFFFu;
 constexpr uint32_t IREF_FAST = 0x40000000u;     // leaf = one triangle with pos 0 and identity rotation
 constexpr uint32_t IREF_MAX_LEAF_PRIMS = 64;   // 6 bits (24..29)
 constexpr uint32_t IREF_MAX_PRIMS = 1u << 24;
+constexpr uint32_t kIndexNodeF4 = RTC_NODE_CONES ? 6 : 4;  // float4 per index node
 
 Aabb aabb_of_primitive(const Primitive& p);  // AABB_t::AABB_t(const Primitive&) src/bvh.cpp:41-87
 

@@ -88,20 +88,20 @@ int emu_frame_linear(void* h, float* out) {
 void emu_scene_free(void* h) { delete (EmuScene*)h; }
 
 void emu_intersect(void* h, long n, const float* o, const float* d, int mode, int32_t* id, float* t, float* nrm,
-                   int32_t* interior, uint64_t* stats /* visits, fallbacks */) {
+                   int32_t* interior, uint64_t* stats /* visits, fallbacks, primitive tests */) {
     EmuScene* e = (EmuScene*)h;
-    uint64_t visits = 0, fallbacks = 0;
-#pragma omp parallel for schedule(dynamic, 256) reduction(+ : visits, fallbacks)
+    uint64_t visits = 0, fallbacks = 0, tests = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : visits, fallbacks, tests)
     for (long i = 0; i < n; ++i) {
-        uint32_t v = 0, f = 0;
+        uint32_t v = 0, f = 0, pt = 0;
         vec3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-        SceneHit hit = mode == 1 ? scene_intersect<1>(e->dev, ro, rd, &v, nullptr, &f) : scene_intersect<0>(e->dev, ro, rd, &v, nullptr, &f);
+        SceneHit hit = mode == 1 ? scene_intersect<1>(e->dev, ro, rd, &v, &pt, &f) : scene_intersect<0>(e->dev, ro, rd, &v, &pt, &f);
         id[i] = hit.id; t[i] = hit.t;
         nrm[3 * i] = hit.n.x; nrm[3 * i + 1] = hit.n.y; nrm[3 * i + 2] = hit.n.z;
         interior[i] = hit.interior;
-        visits += v; fallbacks += f;
+        visits += v; fallbacks += f; tests += pt;
     }
-    if (stats) { stats[0] = visits; stats[1] = fallbacks; }
+    if (stats) { stats[0] = visits; stats[1] = fallbacks; stats[2] = tests; }
 }
 void emu_camera_rays(void* h, long n, const float* xy, float* o, float* d) {
     EmuScene* e = (EmuScene*)h;

@@ -50,7 +50,7 @@ def emu():
 def emu_intersect(L, h, o, d, mode):
     n = len(o)
     pid = np.zeros(n, np.int32); t = np.zeros(n, np.float32); nrm = np.zeros((n, 3), np.float32)
-    inter = np.zeros(n, np.int32); st = np.zeros(2, np.uint64)
+    inter = np.zeros(n, np.int32); st = np.zeros(3, np.uint64)
     L.emu_intersect(h, n, np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32), mode, pid, t, nrm, inter, st)
     return pid, t, nrm, inter, st
 

@@ -15,10 +15,10 @@ static float half_up_(float v){ __half h=__float2half_ru(v); return __half2float
 int main(int argc,char**argv){
   EmuScene* e=(EmuScene*)emu_scene_load(argv[1]);
   const FlatScene& F=e->host.flat; DevScene& S=e->dev;
-  size_t nn=F.inodes.size()/4;
+  size_t nn=F.inodes.size()/kIndexNodeF4;
   std::vector<Node> ex(nn);
   // decode refs
-  for(size_t i=0;i<nn;i++){ const uint32_t* w=(const uint32_t*)&F.inodes[4*i]; for(int c=0;c<4;c++) ex[i].ref[c]=w[12+c]; }
+  for(size_t i=0;i<nn;i++){ const uint32_t* w=(const uint32_t*)&F.inodes[kIndexNodeF4*i]; for(int c=0;c<4;c++) ex[i].ref[c]=w[12+c]; }
   // exact boxes bottom-up (recursive)
   std::function<void(uint32_t,float*,float*)> boxof=[&](uint32_t ref,float*lo,float*hi){
     if(ref&IREF_LEAF){ uint32_t first=ref&0xFFFFFF; const f4&a=F.ubox[2*first],&b=F.ubox[2*first+1]; lo[0]=a.x;lo[1]=a.y;lo[2]=a.z;hi[0]=b.x;hi[1]=b.y;hi[2]=b.z; return;}

@@ -262,32 +262,53 @@ struct IndexBuilder {
     uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth, Cone& cone) {
         max_depth = std::max(max_depth, depth);
         if (hi - lo == 1) { cone = units[order[lo]].cone; return leaf_ref(units[order[lo]]); }
+        // Split cost = sum over the two sides of P(a random ray enters the side) * units in it, with
+        // P = surface of the box * fraction of directions inside the feasibility cone.  Candidate orders: the
+        // unit centres along x, y, z (keys 3..5, |axis.x|, |axis.y|, |axis.z| of the units' cones, would group
+        // faces of one orientation where the surface folds back on itself; the greedy cost never profits).
+        constexpr int kKeys = 3;        // + |axis| of the cones as three more orders: measured, no gain (5.35 vs 5.32 visits)
+        constexpr bool kConeCost = true;  // 5.54 -> 5.32 index node visits per random ray at 100k triangles
+        auto key_of = [&](uint32_t u, int key) -> float {
+            if (key < 3) return idx(units[u].centre, key);
+            const Cone& c = units[u].cone;
+            if (c.open()) return -1.f;
+            return (float)std::fabs(key == 3 ? c.ax : key == 4 ? c.ay : c.az);
+        };
+        auto sort_by = [&](int key) {
+            std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
+                float ca = key_of(a, key), cb = key_of(b, key);
+                return ca < cb || (ca == cb && a < b);
+            });
+        };
+        auto frac = [&](const Cone& c) -> float { return (!kConeCost || c.open()) ? 1.f : (float)(1.0 - std::cos(c.alpha)); };
         float best = 3.0e38f;
         int best_axis = -1;
         uint32_t best_cut = 0;
-        for (int axis = 0; axis < 3; ++axis) {
-            std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
-                float ca = idx(units[a].centre, axis), cb = idx(units[b].centre, axis);
-                return ca < cb || (ca == cb && a < b);
-            });
+        for (int key = 0; key < kKeys; ++key) {
+            sort_by(key);
             Aabb r = empty_box();
-            for (uint32_t i = hi - 1; i > lo; --i) { grow(r, units[order[i]].box); rarea[i] = surface(r); }
+            Cone rc;
+            for (uint32_t i = hi - 1; i > lo; --i) {
+                const Unit& u = units[order[i]];
+                grow(r, u.box);
+                rc = (i == hi - 1) ? u.cone : merge_cones(rc, u.cone);
+                rarea[i] = surface(r) * frac(rc);
+            }
             Aabb l = empty_box();
+            Cone lc;
             for (uint32_t i = lo + 1; i < hi; ++i) {
-                grow(l, units[order[i - 1]].box);
-                float c = surface(l) * (i - lo) + rarea[i] * (hi - i);
-                if (c < best) { best = c; best_axis = axis; best_cut = i; }
+                const Unit& u = units[order[i - 1]];
+                grow(l, u.box);
+                lc = (i == lo + 1) ? u.cone : merge_cones(lc, u.cone);
+                float c = surface(l) * frac(lc) * (i - lo) + rarea[i] * (hi - i);
+                if (c < best) { best = c; best_axis = key; best_cut = i; }
             }
         }
         if (best_axis < 0) {  // every candidate cost was NaN/inf (degenerate boxes): split in the middle
-            best_axis = 2;
+            best_axis = kKeys - 1;
             best_cut = lo + (hi - lo) / 2;
         }
-        if (best_axis != 2)
-            std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
-                float ca = idx(units[a].centre, best_axis), cb = idx(units[b].centre, best_axis);
-                return ca < cb || (ca == cb && a < b);
-            });
+        if (best_axis != kKeys - 1) sort_by(best_axis);
         // binary node in a temporary tree; emit() collapses it to 4-wide nodes afterwards
         uint32_t me = (uint32_t)tmp.size();
         tmp.push_back(Bin{});
@@ -314,12 +335,14 @@ struct IndexBuilder {
     uint32_t emit(uint32_t b, uint32_t depth) {
         wide_depth = std::max(wide_depth, depth);
         struct Slot { Aabb box; uint32_t ref; Cone cone; };
+        // how often a random ray enters the slot: surface of the box * fraction of directions inside its cone
+        auto entered = [](const Slot& sl) { return surface(sl.box) * (sl.cone.open() ? 1.f : (float)(1.0 - std::cos(sl.cone.alpha))); };
         std::vector<Slot> slots = {{tmp[b].box[0], tmp[b].ref[0], tmp[b].cone[0]}, {tmp[b].box[1], tmp[b].ref[1], tmp[b].cone[1]}};
         while (slots.size() < 4) {
             int pick = -1;
             float area = -1.f;
             for (size_t i = 0; i < slots.size(); ++i)
-                if (!(slots[i].ref & IREF_LEAF) && surface(slots[i].box) > area) { area = surface(slots[i].box); pick = (int)i; }
+                if (!(slots[i].ref & IREF_LEAF) && entered(slots[i]) > area) { area = entered(slots[i]); pick = (int)i; }
             if (pick < 0) break;
             const Bin& c = tmp[slots[pick].ref];
             slots[pick] = Slot{c.box[0], c.ref[0], c.cone[0]};

@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--ref-height", type=int, default=64)
     ap.add_argument("--ref-spp", type=int, default=8)
     ap.add_argument("--traversal", type=int, default=0)
-    ap.add_argument("--no-pipeline", action="store_true", help="render the timed frames strictly one after the other")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="keep two frames in flight on two streams (measured: +0.8 %% before the cone nodes, +0.1 %% after; off by default)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,7 +258,7 @@ def main():
 
     # ---- warm-up (also sizes the wavefront buffers), then an untimed instrumented pass
     for i in range(max(args.warmup, 3)):
-        render_step(i, False, not args.no_pipeline)
+        render_step(i, False, args.pipeline)
     barrier()
     scene.reset_counters()
     scene.set_profiling(kernel_events=False, count_visits=True)
@@ -269,7 +270,7 @@ def main():
     scene.reset_counters()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_total, _ = timed(args.steps, False, 100, pipelined=not args.no_pipeline)
+    ms_total, _ = timed(args.steps, False, 100, pipelined=args.pipeline)
     clocks = sampler.result()
     cnt = scene.counters()
     # ---- the same steps again with CUDA events around every kernel (roofline durations)
@@ -344,7 +345,7 @@ def main():
                            "paths_per_step": npix * spp, "triangles": scene.nbvh, "parallelism": "spp-shard x%d" % world,
                            "l2": "wavefront state (%.0f MB/step) exceeds the 126 MB L2" % (min(npix * (hi - lo), 1 << 23) * 148 / 1e6),
                            "traversal": "index" if args.traversal == 0 else "reftree",
-                           "frames_in_flight": 1 if args.no_pipeline else 2},
+                           "frames_in_flight": 2 if args.pipeline else 1},
                 "mrays_per_s": mrays, "rays_per_path": total_rays / max(total_paths, 1),
                 "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": int(npix * 3), "ms_per_step": e2e_ms / args.steps},

@@ -61,7 +61,8 @@ RT_D vec3 normal_vec(uint4 b) {
     float z0, z1, z2, z3;
     box_muller(b.x, b.y, z0, z1);
     box_muller(b.z, b.w, z2, z3);
-    return normalize(mk3(z0, z1, z2));
+    float k = rsqrtf(z0 * z0 + z1 * z1 + z2 * z2);  // a random direction: 2 ulp of rsqrt are immaterial
+    return mk3(z0 * k, z1 * k, z2 * k);
 }
 
 // ------------------------------------------------------------------------------- primitives
@@ -227,7 +228,7 @@ RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t)
     return ok;
 }
 // Primitive::Intersect, src/primitives.cpp:14-52 (normal back to world space, re-normalised)
-template <bool FAST = false, uint32_t FEAT = FE_ALL>
+template <bool FAST = false, uint32_t FEAT = FE_ALL, bool FAST_NORMAL = FAST>
 RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect& out) {
     uint32_t flags = prim_flags_for<FEAT>(S, prim);
     to_local(S, prim, flags, o, d);
@@ -255,7 +256,7 @@ RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect
         q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
         out.n = rotate_exact(q, out.n);
     }
-    out.n = rt_normalize<FAST>(out.n);
+    out.n = rt_normalize<FAST_NORMAL>(out.n);
     return true;
 }
 
@@ -463,8 +464,8 @@ RT_D uint32_t pack_half2(float a, float b) {
 RT_D ConeDir cone_dir(vec3 d) {
     // scale by the largest component first: |d|^2 must neither overflow nor vanish
     float m = fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fabsf(d.z));
-    vec3 e = d * (1.f / m);
-    float k = 1.f / sqrtf(dot(e, e));
+    vec3 e = d * __fdividef(1.f, m);
+    float k = rsqrtf(dot(e, e));  // the result is rounded to 11 bits
     ConeDir c;
     c.xy = pack_half2(e.x * k, e.y * k);
     c.zz = pack_half2(e.z * k, e.z * k);
@@ -698,8 +699,10 @@ RT_D bool light_intersect(const DevScene& S, uint32_t prim, bool is_box, vec3 o,
 RT_D vec3 sample_cosine(const Rng& g, vec3 n) {
     vec3 dir = normal_vec(g.block(1)) + n;
     if (dot(dir, n) <= 1e-8f) return n;
-    if (length(dir) <= 1e-4f) return n;
-    return normalize(dir);
+    float dd = dot(dir, dir);
+    if (dd <= 1e-8f) return n;  // length(dir) <= 1e-4
+    float k = rsqrtf(dd);
+    return mk3(dir.x * k, dir.y * k, dir.z * k);
 }
 // Distribution::SampleBox, src/distributions.cpp:227-269
 template <uint32_t FEAT = FE_ALL>
@@ -722,7 +725,7 @@ RT_D vec3 sample_box(const DevScene& S, uint32_t prim, const Rng& g, vec3 x) {
         else if (u < wx + wy) pnt.y = side * s.y;
         else pnt.z = side * s.z;
         vec3 on_box = ((FEAT & FE_ROTATION) ? rotate(q, pnt) : pnt) + pos;  // rotate(identity, v) == v exactly
-        smp = normalize(on_box - x);
+        smp = rt_normalize<true>(on_box - x);
         Isect is;
         if (light_intersect<FEAT>(S, prim, true, x, smp, is)) break;
     }
@@ -816,12 +819,13 @@ RT_D float pdf_light(const DevScene& S, uint32_t prim, vec3 x, vec3 d) {
     quat q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
     const float dd = dot(d, d);
     const float p_y = __fdividef(1.f, 8.f * (g.x * g.x + g.y * g.y + g.z * g.z));
+    const vec3 ginv = mk3(__fdividef(1.f, g.x), __fdividef(1.f, g.y), __fdividef(1.f, g.z));
     float sum = 0.f;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
         const float t = which == 0 ? t_first : t_out;
         if (which == 1 && (inside || t_out - (t_in + 1e-4f) < 0.f)) break;
-        vec3 nl = (lo + t * ld) / g;  // face normal as Primitive::IntersectBox finds it
+        vec3 nl = (lo + t * ld) * ginv;  // face normal as Primitive::IntersectBox finds it (p / s, largest component)
         float mx = fmaxf(fmaxf(fabsf(nl.x), fabsf(nl.y)), fabsf(nl.z));
         nl = mk3(fabsf(nl.x) != mx ? 0.f : nl.x, fabsf(nl.y) != mx ? 0.f : nl.y, fabsf(nl.z) != mx ? 0.f : nl.z);
         nl = rt_normalize<true>(nl);

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
             uint32_t prim = WF_LD(H.id + i);
             Isect is;
             vec3 o = ld3(WF_LD(P.o + i)), d = ld3(WF_LD(P.d + i));
-            if (prim == HIT_MISS || !prim_intersect<false, FEAT>(S, prim, o, d, is)) {
+            if (prim == HIT_MISS || !prim_intersect<false, FEAT, true>(S, prim, o, d, is)) {  // exact t, rsqrt normal
                 L = L + beta * mk3(S.bg.x, S.bg.y, S.bg.z);  // src/scene.cpp:92-94
             } else {
                 bool interior = is.interior != 0;

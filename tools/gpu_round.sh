@@ -9,8 +9,8 @@ timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/te
 tail -3 gpurun_out/tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_main.log 2>&1
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pipeline > gpurun_out/bench_nopipe.log 2>&1
-for f in main nopipe; do
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --pipeline > gpurun_out/bench_pipe.log 2>&1
+for f in main pipe; do
   tail -1 gpurun_out/bench_$f.log | python -c '
 import sys, json
 d = json.loads(sys.stdin.read()); r = d["roofline"]

@@ -199,10 +199,10 @@ def main():
     # spp sharding: rank r renders samples [lo, hi)
     lo, hi = rtc.shard_samples(spp, rank, world)
     npix = W * H
-    # Frames are pipelined two deep: frame i+1 starts on the other stream (own accumulation buffer) while the
-    # last kernels of frame i drain, so the tail of a persistent k_traverse launch -- a few long rays on an
-    # otherwise idle GPU -- overlaps the next frame's first kernels instead of ending the step.  Every frame is
-    # still rendered, reduced and complete inside the timed region.
+    # --pipeline: frames two deep, frame i+1 starts on the other stream (own accumulation buffer) while the last
+    # kernels of frame i drain, so the tail of a persistent k_traverse launch overlaps the next frame's first
+    # kernels.  Every frame is still rendered, reduced and complete inside the timed region.  Default: one frame
+    # at a time.
     accums = [torch.zeros(npix * 3, dtype=torch.float32, device=dev) for _ in range(2)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
     rgb = torch.zeros(npix * 3, dtype=torch.uint8, device=dev)

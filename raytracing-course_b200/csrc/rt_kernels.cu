@@ -138,8 +138,11 @@ constexpr int kVisitQuorum = RTC_VISIT_QUORUM;
 #define RTC_LAZY_OVERFLOW 1
 #endif  // at least this many lanes ready to visit: skip the full vote
 
+#ifndef RTC_TRAVERSE_MIN_BLOCKS
+#define RTC_TRAVERSE_MIN_BLOCKS 7   // 72 registers; 5 / 6 / 8 blocks (84 / 79 / 64 registers): 12.96 / 11.73 / 12.75 ms against 11.56
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
+__global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
                                                    uint32_t* cursor, unsigned long long* stats) {
     const uint32_t total = *tq_count;
     const uint32_t lane = threadIdx.x & 31;

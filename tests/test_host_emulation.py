@@ -182,3 +182,77 @@ def test_feature_specialised_shading_is_bit_identical(emu, name, features):
         for a, b in zip(full, part):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, feat)
     emu.emu_scene_free(h)
+
+
+def _soup_scene(rng, ntri, scale, size, sliver=False, near_origin=False):
+    """hw5 scene text: `ntri` untransformed triangles of about `size` inside a cube of half-width `scale`."""
+    lines = ["DIMENSIONS 8 8", "RAY_DEPTH 2", "SAMPLES 1", "BG_COLOR 0 0 0", "CAMERA_POSITION 0 0 %g" % (3 * scale),
+             "CAMERA_RIGHT 1 0 0", "CAMERA_UP 0 1 0", "CAMERA_FORWARD 0 0 -1", "CAMERA_FOV_X 1", ""]
+    tris = []
+    for _ in range(ntri):
+        c = rng.uniform(-scale, scale, 3)
+        if near_origin:
+            c *= 0.02
+        e1, e2 = rng.normal(size=3) * size, rng.normal(size=3) * size
+        if sliver:
+            e2 = e1 * rng.uniform(0.3, 0.9) + rng.normal(size=3) * size * 1e-3
+        a, b, cc = c, c + e1, c + e2
+        tris.append(np.stack([a, b, cc]).astype(np.float32))
+        v = tris[-1].reshape(-1)
+        lines += ["NEW_PRIMITIVE", "TRIANGLE " + " ".join(repr(float(x)) for x in v), "COLOR 0.5 0.5 0.5", ""]
+    return "\n".join(lines) + "\n", np.stack(tris).astype(np.float64)
+
+
+def _aimed_rays(rng, T, n):
+    """Rays built to HIT: through a point of the rendered triangle T' = T - (a.n) n and a point of the real
+    triangle's AABB (corners included) -- the extreme directions of the feasibility cone."""
+    a, b, c = T[:, 0], T[:, 1], T[:, 2]
+    nrm = np.cross(b - a, c - a)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-300)
+    h = (a * nrm).sum(1, keepdims=True)
+    idx = rng.integers(0, len(T), n)
+    u = rng.uniform(0.02, 0.96, n); v = rng.uniform(0.02, 0.98, n) * (1 - u)
+    q = a[idx] + u[:, None] * (b[idx] - a[idx]) + v[:, None] * (c[idx] - a[idx])
+    p = q - h[idx] * nrm[idx]                                   # on T'
+    mn, mx = T[idx].min(1), T[idx].max(1)
+    w = rng.uniform(0, 1, (n, 3))
+    # half of the coordinates sit next to a box face (2 % inside: exactly ON the face is the documented ulp case
+    # where the min/max * (1/d) slab test and the reference's centre/half division may disagree)
+    w = np.where(rng.uniform(size=(n, 3)) < 0.5, 0.02 + 0.96 * np.round(w), w)
+    x = mn + w * (mx - mn)
+    d = x - p
+    flip = rng.uniform(size=n) < 0.5
+    d[flip] *= -1
+    o = p - d * rng.uniform(0.2, 3.0, n)[:, None]                # the hit is at t > 0 either way
+    ok = np.linalg.norm(d, axis=1) > 0
+    return o[ok].astype(np.float32), d[ok].astype(np.float32)
+
+
+@pytest.mark.parametrize("case", ["plain", "tiny", "huge", "sliver", "near_origin", "few"])
+def test_feasibility_cones_never_cull_a_hit(emu, case):
+    """Index traversal (with the per-child direction cones) against the walk over the reference's own tree on
+    triangle soups of several scales, with rays aimed through the rendered triangle and the corners of the real
+    triangle's box (just inside its corners), and with random rays: identical primitive ids (up to the documented ulp grazing cases)."""
+    rng = np.random.default_rng({"plain": 1, "tiny": 2, "huge": 3, "sliver": 4, "near_origin": 5, "few": 6}[case])
+    kw = {"plain": dict(ntri=3000, scale=5.0, size=0.1), "tiny": dict(ntri=2000, scale=5e-3, size=2e-4),
+          "huge": dict(ntri=2000, scale=3e3, size=40.0), "sliver": dict(ntri=2000, scale=5.0, size=0.2, sliver=True),
+          "near_origin": dict(ntri=2000, scale=5.0, size=0.1, near_origin=True), "few": dict(ntri=3, scale=2.0, size=0.5)}[case]
+    text, T = _soup_scene(rng, **kw)
+    raw = text.encode()
+    h = emu.emu_scene_parse_dialect(raw, len(raw), 5)
+    assert h
+    o1, d1 = _aimed_rays(rng, T, 60000)
+    n2 = 40000
+    o2 = rng.uniform(-1.5 * kw["scale"], 1.5 * kw["scale"], (n2, 3)).astype(np.float32)
+    d2 = rng.normal(size=(n2, 3)).astype(np.float32)
+    for o, d, need_hits in ((o1, d1, True), (o2, d2, False)):
+        a = emu_intersect(emu, h, o, d, 0)
+        b = emu_intersect(emu, h, o, d, 1)
+        same = a[0] == b[0]
+        assert same.mean() >= 0.9995, (case, same.mean(), np.nonzero(~same)[0][:5])
+        # a ray the index traversal loses entirely (hit in the reference walk, none here) would be a wrong cull:
+        lost = (a[0] < 0) & (b[0] >= 0)
+        assert lost.mean() <= 2e-4, (case, lost.sum())
+        if need_hits:
+            assert (b[0] >= 0).mean() > 0.5, (case, (b[0] >= 0).mean())
+    emu.emu_scene_free(h)

@@ -246,6 +246,7 @@ struct IndexBuilder {
     std::vector<f4>& out;  // 4 f4 (64 bytes) per 4-wide node
     std::vector<float> rarea;
     uint32_t max_depth = 0;
+    double slack = 0;  // absolute inflation of every child half-extent: 2^-20 of the scene size (set by HostScene::init)
 
     static uint32_t leaf_ref(const Unit& u) { return IREF_LEAF | (u.fast ? IREF_FAST : 0u) | ((u.count - 1) << 24) | u.first; }
     static f4 bits4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -363,7 +364,10 @@ struct IndexBuilder {
             for (int a = 0; a < 3; ++a) {
                 uint16_t c16 = half_bits_rn(0.5f * (mn[a] + mx[a]));
                 double c = (double)half_to_float(c16);
-                double need = std::max((double)mx[a] - c, c - (double)mn[a]);
+                // + slack: the device evaluates fma(c, 1/d, -(o * 1/d)) -+ h |1/d|, whose rounding is a few ulp of
+                // |o / d| and |c / d|, i.e. a few 2^-24 of the scene size in world units; the child boxes must stay
+                // conservative even when a face is exactly representable in fp16 (no rounding margin of its own)
+                double need = std::max((double)mx[a] - c, c - (double)mn[a]) + slack;
                 float nf = (float)need;
                 if ((double)nf < need) nf = std::nextafter(nf, INFINITY);
                 hv[a][i] = c16;
@@ -545,6 +549,11 @@ void HostScene::init() {
     F.iroot = IREF_NONE;
     if (!units.empty()) {
         IndexBuilder ib{units, {}, F.inodes, std::vector<float>(units.size() + 1, 0.f)};
+        double extent = std::max({std::fabs((double)cam.pos.x), std::fabs((double)cam.pos.y), std::fabs((double)cam.pos.z)});
+        for (const Unit& u : units)
+            for (float v : {u.box.mn.x, u.box.mn.y, u.box.mn.z, u.box.mx.x, u.box.mx.y, u.box.mx.z})
+                if (std::isfinite(v)) extent = std::max(extent, (double)std::fabs(v));
+        ib.slack = extent * (1.0 / 1048576.0);
         ib.order.resize(units.size());
         std::iota(ib.order.begin(), ib.order.end(), 0u);
         Cone whole;

@@ -542,20 +542,34 @@ RT_D void leaf_best(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, 
     if (tests) *tests += count;
 }
 
+// AABB_t::Intersect of a reference LEAF from its stored corners, in the reference's own arithmetic
+// (src/bvh.cpp:89-93: s = 0.5 (max - min), centre = 0.5 (max + min), IntersectBox(ray - centre, s) with IEEE
+// divisions, src/primitives.cpp:70-97): hit and the entry distance (-inf when the origin is inside the box).
+RT_D void leaf_box_reference(vec3 mn, vec3 mx, vec3 o, vec3 d, bool& hit, float& tc) {
+    const vec3 s = 0.5f * (mx - mn), c = 0.5f * (mx + mn);
+    const vec3 oc = o - c;
+    const vec3 a = (-s - oc) / d, b = (s - oc) / d;
+    const float t1 = fmaxf(fmaxf(fminf(a.x, b.x), fminf(a.y, b.y)), fminf(a.z, b.z));
+    const float t2 = fminf(fminf(fmaxf(a.x, b.x), fmaxf(a.y, b.y)), fmaxf(a.z, b.z));
+    hit = !(t1 > t2) && !(t2 < 0.f);
+    tc = t1 < 0.f ? -kInfF : t1;
+}
+
 // One candidate leaf: the EXACT box of the reference leaf first (a single untransformed triangle
 // has min/max of its vertices as its reference AABB, src/bvh.cpp:53-64; other leaves keep theirs in
-// ubox), then its primitives.  Returns false when the ray misses the exact box.
-RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, vec3 inv, vec3 oi, float& bt, int& bid, float& tc,
-                    uint32_t* tests) {
+// ubox), tested with the reference's arithmetic -- the fp16 child boxes of the index nodes only ever ADD
+// candidates, so the set of leaves that pass here is exactly the set BVH_t::Intersect_ would reach -- then
+// its primitives.  Returns false when the ray misses the exact box.
+RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, int& bid, float& tc, uint32_t* tests) {
     const uint32_t first = ref & 0xFFFFFFu;
     bt = kInfF;
     bid = -1;
     bool hitbox;
     if (ref & IREF_FAST) {
         float4 g0 = ldg4(S.geo0 + first), g1 = ldg4(S.geo1 + first), g2 = ldg4(S.geo2 + first);
-        slab(fminf(fminf(g0.x, g1.x), g2.x), fminf(fminf(g0.y, g1.y), g2.y), fminf(fminf(g0.z, g1.z), g2.z),
-             fmaxf(fmaxf(g0.x, g1.x), g2.x), fmaxf(fmaxf(g0.y, g1.y), g2.y), fmaxf(fmaxf(g0.z, g1.z), g2.z),
-             inv, oi, ref, hitbox, tc);
+        leaf_box_reference(mk3(fminf(fminf(g0.x, g1.x), g2.x), fminf(fminf(g0.y, g1.y), g2.y), fminf(fminf(g0.z, g1.z), g2.z)),
+                           mk3(fmaxf(fmaxf(g0.x, g1.x), g2.x), fmaxf(fmaxf(g0.y, g1.y), g2.y), fmaxf(fmaxf(g0.z, g1.z), g2.z)),
+                           o, d, hitbox, tc);
         if (!hitbox) return false;
         float t; bool interior;
         if (isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), mk3(g0.w, g1.w, g2.w), t, interior)) { bt = t; bid = (int)first; }
@@ -563,7 +577,7 @@ RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, vec3 inv, v
         return true;
     }
     float4 bmn = ldg4(S.ubox + 2 * (size_t)first), bmx = ldg4(S.ubox + 2 * (size_t)first + 1);
-    slab(bmn.x, bmn.y, bmn.z, bmx.x, bmx.y, bmx.z, inv, oi, ref, hitbox, tc);
+    leaf_box_reference(ld3(bmn), ld3(bmx), o, d, hitbox, tc);
     if (!hitbox) return false;
     leaf_best(S, ref, o, d, bt, bid, tests);
     return true;
@@ -586,7 +600,7 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
     for (;;) {
         if (ref & IREF_LEAF) {
             float bt, tc; int bid;
-            if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, tests) && bid >= 0) {
+            if (leaf_test(S, ref, o, d, bt, bid, tc, tests) && bid >= 0) {
                 if (k == kMaxRecords) return false;
                 rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc;
                 ++k;

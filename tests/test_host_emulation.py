@@ -203,7 +203,7 @@ def _soup_scene(rng, ntri, scale, size, sliver=False, near_origin=False):
     return "\n".join(lines) + "\n", np.stack(tris).astype(np.float64)
 
 
-def _aimed_rays(rng, T, n):
+def _aimed_rays(rng, T, n, inset=0.02):
     """Rays built to HIT: through a point of the rendered triangle T' = T - (a.n) n and a point of the real
     triangle's AABB (corners included) -- the extreme directions of the feasibility cone."""
     a, b, c = T[:, 0], T[:, 1], T[:, 2]
@@ -216,9 +216,9 @@ def _aimed_rays(rng, T, n):
     p = q - h[idx] * nrm[idx]                                   # on T'
     mn, mx = T[idx].min(1), T[idx].max(1)
     w = rng.uniform(0, 1, (n, 3))
-    # half of the coordinates sit next to a box face (2 % inside: exactly ON the face is the documented ulp case
-    # where the min/max * (1/d) slab test and the reference's centre/half division may disagree)
-    w = np.where(rng.uniform(size=(n, 3)) < 0.5, 0.02 + 0.96 * np.round(w), w)
+    # half of the coordinates sit next to a box face (`inset` of the box inside it; 0 = exactly ON the face, where
+    # only the reference's own centre/half arithmetic reproduces the reference's decision)
+    w = np.where(rng.uniform(size=(n, 3)) < 0.5, inset + (1 - 2 * inset) * np.round(w), w)
     x = mn + w * (mx - mn)
     d = x - p
     flip = rng.uniform(size=n) < 0.5

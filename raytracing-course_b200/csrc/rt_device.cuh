@@ -14,6 +14,11 @@
 namespace rtc {
 
 #define RT_D __device__ __forceinline__
+#ifdef __CUDACC__
+#define RT_D_COLD static __device__ __noinline__   // rarely taken paths: one out-of-line copy per kernel
+#else
+#define RT_D_COLD static inline                    // host compilation of this header (tests/host_emul)
+#endif
 
 constexpr float kInfF = 1e18f;      // include/bvh.h:9
 constexpr float kPi = 3.14159274101257324f;  // (float)acos(-1), include/distributions.h:14
@@ -545,7 +550,7 @@ RT_D void leaf_best(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, 
 // AABB_t::Intersect of a reference LEAF from its stored corners, in the reference's own arithmetic
 // (src/bvh.cpp:89-93: s = 0.5 (max - min), centre = 0.5 (max + min), IntersectBox(ray - centre, s) with IEEE
 // divisions, src/primitives.cpp:70-97): hit and the entry distance (-inf when the origin is inside the box).
-RT_D void leaf_box_reference(vec3 mn, vec3 mx, vec3 o, vec3 d, bool& hit, float& tc) {
+RT_D_COLD void leaf_box_reference(vec3 mn, vec3 mx, vec3 o, vec3 d, bool& hit, float& tc) {  // rare: kept out of line
     const vec3 s = 0.5f * (mx - mn), c = 0.5f * (mx + mn);
     const vec3 oc = o - c;
     const vec3 a = (-s - oc) / d, b = (s - oc) / d;
@@ -555,31 +560,58 @@ RT_D void leaf_box_reference(vec3 mn, vec3 mx, vec3 o, vec3 d, bool& hit, float&
     tc = t1 < 0.f ? -kInfF : t1;
 }
 
+// Leaf box test = the reference's decision at FMA cost: the min/max * (1/d) slab form first; its rounding error is
+// a few ulp of its operands, so a result further than 2e-6 * (|o/d| + |t|) from every decision boundary (t1 = t2,
+// t2 = 0, t1 = 0) is the reference's result as well, and only a ray inside that band (it grazes a face or starts
+// on one) pays for leaf_box_reference (IEEE divisions were 5 % of k_traverse when every candidate took them).
+RT_D void leaf_box(vec3 mn, vec3 mx, vec3 o, vec3 d, vec3 inv, vec3 oi, bool& hit, float& tc) {
+    float x1 = fmaf(mn.x, inv.x, -oi.x), x2 = fmaf(mx.x, inv.x, -oi.x);
+    float y1 = fmaf(mn.y, inv.y, -oi.y), y2 = fmaf(mx.y, inv.y, -oi.y);
+    float z1 = fmaf(mn.z, inv.z, -oi.z), z2 = fmaf(mx.z, inv.z, -oi.z);
+    float t1 = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    float t2 = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    const float band = 2e-6f * (fabsf(oi.x) + fabsf(oi.y) + fabsf(oi.z) + fabsf(t1) + fabsf(t2));
+#ifdef RTC_LEAF_BOX_FAST_ONLY   // A/B: never take the exact path (the pre-session-3 behaviour)
+    const bool clear = band == band || true;
+#else
+    const bool clear = fabsf(t2 - t1) > band && fabsf(t2) > band && fabsf(t1) > band;  // NaN / inf: not clear
+#endif
+    if (!clear) { leaf_box_reference(mn, mx, o, d, hit, tc); return; }
+    hit = t1 <= t2 && t2 >= 0.f;
+    tc = t1 < 0.f ? -kInfF : t1;
+}
+
 // One candidate leaf: the EXACT box of the reference leaf first (a single untransformed triangle
 // has min/max of its vertices as its reference AABB, src/bvh.cpp:53-64; other leaves keep theirs in
-// ubox), tested with the reference's arithmetic -- the fp16 child boxes of the index nodes only ever ADD
-// candidates, so the set of leaves that pass here is exactly the set BVH_t::Intersect_ would reach -- then
-// its primitives.  Returns false when the ray misses the exact box.
-RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, float& bt, int& bid, float& tc, uint32_t* tests) {
+// ubox) -- the fp16 child boxes of the index nodes only ever ADD candidates, so the set of leaves that pass here
+// is the set BVH_t::Intersect_ would reach (unless the ray grazes an ANCESTOR's face within an ulp) -- then its
+// primitives.  Returns false when the ray misses the exact box.
+RT_D bool leaf_test(const DevScene& S, uint32_t ref, vec3 o, vec3 d, vec3 inv, vec3 oi, float& bt, int& bid, float& tc,
+                    uint32_t* tests) {
     const uint32_t first = ref & 0xFFFFFFu;
+    const bool fast = (ref & IREF_FAST) != 0;
     bt = kInfF;
     bid = -1;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+    vec3 mn, mx;
+    if (fast) {
+        g0 = ldg4(S.geo0 + first); g1 = ldg4(S.geo1 + first); g2 = ldg4(S.geo2 + first);
+        mn = mk3(fminf(fminf(g0.x, g1.x), g2.x), fminf(fminf(g0.y, g1.y), g2.y), fminf(fminf(g0.z, g1.z), g2.z));
+        mx = mk3(fmaxf(fmaxf(g0.x, g1.x), g2.x), fmaxf(fmaxf(g0.y, g1.y), g2.y), fmaxf(fmaxf(g0.z, g1.z), g2.z));
+    } else {
+        mn = ld3(ldg4(S.ubox + 2 * (size_t)first));
+        mx = ld3(ldg4(S.ubox + 2 * (size_t)first + 1));
+    }
     bool hitbox;
-    if (ref & IREF_FAST) {
-        float4 g0 = ldg4(S.geo0 + first), g1 = ldg4(S.geo1 + first), g2 = ldg4(S.geo2 + first);
-        leaf_box_reference(mk3(fminf(fminf(g0.x, g1.x), g2.x), fminf(fminf(g0.y, g1.y), g2.y), fminf(fminf(g0.z, g1.z), g2.z)),
-                           mk3(fmaxf(fmaxf(g0.x, g1.x), g2.x), fmaxf(fmaxf(g0.y, g1.y), g2.y), fmaxf(fmaxf(g0.z, g1.z), g2.z)),
-                           o, d, hitbox, tc);
-        if (!hitbox) return false;
+    leaf_box(mn, mx, o, d, inv, oi, hitbox, tc);
+    if (!hitbox) return false;
+    if (fast) {
         float t; bool interior;
         if (isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), mk3(g0.w, g1.w, g2.w), t, interior)) { bt = t; bid = (int)first; }
         if (tests) ++*tests;
-        return true;
+    } else {
+        leaf_best(S, ref, o, d, bt, bid, tests);
     }
-    float4 bmn = ldg4(S.ubox + 2 * (size_t)first), bmx = ldg4(S.ubox + 2 * (size_t)first + 1);
-    leaf_box_reference(ld3(bmn), ld3(bmx), o, d, hitbox, tc);
-    if (!hitbox) return false;
-    leaf_best(S, ref, o, d, bt, bid, tests);
     return true;
 }
 
@@ -600,7 +632,7 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
     for (;;) {
         if (ref & IREF_LEAF) {
             float bt, tc; int bid;
-            if (leaf_test(S, ref, o, d, bt, bid, tc, tests) && bid >= 0) {
+            if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, tests) && bid >= 0) {
                 if (k == kMaxRecords) return false;
                 rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc;
                 ++k;

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 const uint32_t ref = stk[kStackWords - nl];
                 --nl;
                 float bt, tc; int bid;
-                if (leaf_test(S, ref, o, d, bt, bid, tc, STATS ? &tests : nullptr) && bid >= 0) {
+                if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, STATS ? &tests : nullptr) && bid >= 0) {
                     if (k == kMaxRecords) { overflow = true; node = kNone; sp = 0; nl = 0; }
                     else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc; ++k; }
                 }

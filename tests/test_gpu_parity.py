@@ -348,3 +348,30 @@ def test_large_frame_4k(rtc, gpu_scenes):
     img = s.Render(seed=1)
     assert img.shape == (2160, 3840, 3) and img.max() > 0
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["practice5_dragon_10k", "practice5_dragon_100k"])
+def test_rays_aimed_at_the_rendered_triangles(rtc, gpu_scenes, oracle_scenes, name):
+    """Random rays almost never hit the dragon (a triangle is rendered on the plane through the origin but culled
+    by the box of the real one: DESIGN.md 'Feasibility cones').  These rays are built to hit: through a point of
+    the rendered triangle and a point just inside the real triangle's box, i.e. along the extreme directions the
+    cones must let through.  Index traversal, reference-tree walk and oracle must name the same primitive."""
+    from test_host_emulation import _aimed_rays
+    tris = []
+    for line in open(scene_path(name)):
+        if line.startswith("TRIANGLE"):
+            tris.append([float(v) for v in line.split()[1:10]])
+    T = np.array(tris, np.float32).astype(np.float64).reshape(-1, 3, 3)
+    rng = np.random.default_rng(77)
+    o, d = _aimed_rays(rng, T, 150000)
+    s, a = gpu_scenes(name), oracle_scenes(name)
+    fast = s.RayIntersection(o, d, rtc.TRAVERSAL_INDEX)
+    slow = s.RayIntersection(o, d, rtc.TRAVERSAL_REFTREE)
+    bvh_hit = (slow[0] >= 0) & (slow[0] < s.nbvh)
+    assert bvh_hit.mean() > 0.3, bvh_hit.mean()          # the rays do reach triangles
+    assert (fast[0] == slow[0]).mean() >= 0.9999, (fast[0] != slow[0]).sum()
+    k = 30000
+    want = a.intersect(o[:k], d[:k])
+    assert (fast[0][:k] == want[0]).mean() >= 0.9999, (fast[0][:k] != want[0]).sum()
+    check_hits(tuple(x[:k] for x in fast), want, id_agree=0.9999)

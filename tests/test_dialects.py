@@ -15,7 +15,7 @@ import orclib
 from conftest import ROOT, golden
 
 DETERMINISTIC = ["hw1_course_sample6", "hw2_hw2_lights"]
-MONTE_CARLO = ["hw3_course_sample6", "hw4_course_sample6", "hw3_course_sample4", "hw4_course_sample4"]
+MONTE_CARLO = ["hw3_course_sample6", "hw4_course_sample6", "hw3_course_sample4", "hw4_course_sample4", "hw3_course_sample3", "hw4_course_sample3"]
 
 
 def load(fixture):
@@ -164,7 +164,8 @@ def test_gpu_monte_carlo_dialects_vs_reference_images(rtc, oracle_lib, fixture):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fixture,spp", [("hw3_course_sample6", 4), ("hw4_course_sample6", 4), ("hw3_course_sample4", 6), ("hw4_course_sample4", 6)])
+@pytest.mark.parametrize("fixture,spp", [("hw3_course_sample6", 4), ("hw4_course_sample6", 4), ("hw3_course_sample4", 6), ("hw4_course_sample4", 6),
+                                         ("hw3_course_sample3", 6), ("hw4_course_sample3", 6)])
 def test_gpu_monte_carlo_dialects_sample_exact_vs_oracle(rtc, oracle_lib, fixture, spp):
     """Same Philox streams on both sides (the hw3 half-pixel jitter offset and its uniform-hemisphere lobe
     included): per-pixel sums agree to float rounding except where a path crosses a discontinuity differently."""

@@ -242,6 +242,8 @@ def dialects():
     dialect_fixture(4, "course_sample6", 103, 133, 2048)
     dialect_fixture(3, "course_sample4", 64, 64, 4096)
     dialect_fixture(4, "course_sample4", 64, 64, 2048)
+    dialect_fixture(3, "course_sample3", 64, 64, 2048)   # metallic box + emissive box
+    dialect_fixture(4, "course_sample3", 64, 64, 1024)
 
 
 if __name__ == "__main__":

@@ -243,7 +243,7 @@ static uint16_t half_up(float f) {
 struct IndexBuilder {
     const std::vector<Unit>& units;
     std::vector<uint32_t> order;
-    std::vector<f4>& out;  // 4 f4 (64 bytes) per 4-wide node
+    std::vector<f4>& out;  // kIndexNodeF4 f4 (96 bytes) per 4-wide node
     std::vector<float> rarea;
     uint32_t max_depth = 0;
     double slack = 0;  // absolute inflation of every child half-extent: 2^-20 of the scene size (set by HostScene::init)

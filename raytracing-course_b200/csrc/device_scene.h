@@ -18,7 +18,7 @@ struct DevScene {
     const float4* xf_rot;  // quaternion xyzw
     const float4* mat0;    // (colour, bits(material))
     const float4* mat1;    // (emission, ior)
-    // index BVH: 4 float4 (64 B) per 4-wide node, fp16 child boxes
+    // index BVH: 6 float4 (96 B) per 4-wide node: fp16 child boxes, child refs, fp16 child direction cones
     const float4* inodes;
     // reference BVH: 2 float4 per node + meta
     const float4* rnodes;

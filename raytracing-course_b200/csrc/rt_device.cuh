@@ -401,7 +401,8 @@ RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, Leaf
     return cur;
 }
 
-// One index-BVH node = 64 bytes: the boxes of its 4 children as fp16 rounded OUTWARD
+// One index-BVH node = 96 bytes: the boxes of its 4 children as fp16 rounded OUTWARD (64 bytes with the refs) + one
+// direction cone per child (32 bytes, cone_cull_pair below)
 // (min.x[4] min.y[4] min.z[4] max.x[4] | max.y[4] max.z[4] refs[4]), read with two 32-byte loads.
 // The traversal is bound by the L1 misses an SM can keep in flight (profiles/r01_experiments.md),
 // so node bytes are what counts; conservative boxes only add candidates, and every leaf is

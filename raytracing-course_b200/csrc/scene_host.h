@@ -97,7 +97,7 @@ struct FlatScene {
     std::vector<f4> xf_pos;            // (pos.xyz, bits(type|flags))
     std::vector<f4> xf_rot;            // quaternion xyzw
     std::vector<f4> mat0, mat1;        // (col.rgb, bits(material)) (emission.rgb, ior)
-    // index BVH, 4-wide, 64 bytes per node (4 x f4): child boxes as fp16 rounded OUTWARD
+    // index BVH, 4-wide, kIndexNodeF4 x f4 per node (96 bytes): child boxes as fp16 rounded OUTWARD, refs, child cones
     // (min.x[4] min.y[4] min.z[4] max.x[4] | max.y[4] max.z[4] refs[4]); exact leaf boxes: ubox
     std::vector<f4> inodes;
     uint32_t iroot = 0;  // child reference of the root (may be a leaf reference)

@@ -266,7 +266,8 @@ struct IndexBuilder {
         // Split cost = sum over the two sides of P(a random ray enters the side) * units in it, with
         // P = surface of the box * fraction of directions inside the feasibility cone.  Candidate orders: the
         // unit centres along x, y, z (keys 3..5, |axis.x|, |axis.y|, |axis.z| of the units' cones, would group
-        // faces of one orientation where the surface folds back on itself; the greedy cost never profits).
+        // faces of one orientation where the surface folds back on itself; the greedy cost never profits, and forced
+        // 2-means orientation splits below 64 .. 4096 units make it worse: profiles/r01_experiments.md).
         constexpr int kKeys = 3;        // + |axis| of the cones as three more orders: measured, no gain (5.35 vs 5.32 visits)
         constexpr bool kConeCost = true;  // 5.54 -> 5.32 index node visits per random ray at 100k triangles
         auto key_of = [&](uint32_t u, int key) -> float {
@@ -330,24 +331,77 @@ struct IndexBuilder {
     std::vector<Bin> tmp;
     uint32_t wide_depth = 0;
 
-    // Collapses the binary tree rooted at binary node `b` into one 4-wide node: the child with the
-    // largest surface that is still an inner node is replaced by its own two children until four
-    // slots are filled.  Returns the index of the emitted node.
+    // ---- optimal collapse of the binary tree into 4-wide nodes (dynamic programme over the binary tree).
+    // Visiting a wide node costs the same whatever it holds, so the quantity to minimise is the expected number of
+    // wide nodes a random ray enters: sum over wide nodes of P(enter) = surface of its box * fraction of directions
+    // inside its cone.  best[n][k-1] = least such sum for the subtree of binary node n when it may occupy at most k
+    // slots of its parent's wide node: either one slot (n becomes a wide node itself: P(n) + its own best use of 4
+    // slots), or the slots are shared between its two children.  A leaf costs nothing in any number of slots.
+    struct Plan {
+        float cost[4];
+        uint8_t left[4];  // slots given to the left child when the subtree is spread over k slots; 0 = "n is one wide node"
+    };
+    std::vector<Plan> plan;
+    float entered(const Aabb& box, const Cone& cone) const {
+        return surface(box) * (cone.open() ? 1.f : (float)(1.0 - std::cos(cone.alpha)));
+    }
+    float plan_cost(uint32_t ref, int k) const { return (ref & IREF_LEAF) ? 0.f : plan[ref].cost[k - 1]; }
+    void make_plan() {
+        plan.assign(tmp.size(), Plan{});
+        // children have larger indices than their parent (build() pushes the parent first): a reverse sweep sees them first
+        for (size_t n = tmp.size(); n-- > 0;) {
+            const Bin& b = tmp[n];
+            Plan& p = plan[n];
+            float share[5];      // share[k] = least cost of spreading n's two children over exactly k >= 2 slots
+            uint8_t share_left[5];
+            for (int k = 2; k <= 4; ++k) {
+                share[k] = 3.0e38f; share_left[k] = 1;
+                for (int i = 1; i < k; ++i) {
+                    float c = plan_cost(b.ref[0], i) + plan_cost(b.ref[1], k - i);
+                    if (c < share[k]) { share[k] = c; share_left[k] = (uint8_t)i; }
+                }
+                if (k > 2 && share[k - 1] <= share[k]) { share[k] = share[k - 1]; share_left[k] = share_left[k - 1]; }
+            }
+            Aabb whole = b.box[0];
+            grow(whole, b.box[1]);
+            float self = entered(whole, merge_cones(b.cone[0], b.cone[1])) + share[4];
+            if (!(self < 3.0e38f)) self = 3.0e38f;
+            p.cost[0] = self; p.left[0] = 0;
+            for (int k = 2; k <= 4; ++k) {
+                if (share[k] < self) { p.cost[k - 1] = share[k]; p.left[k - 1] = share_left[k]; }
+                else { p.cost[k - 1] = self; p.left[k - 1] = 0; }
+            }
+        }
+    }
+    struct Slot { Aabb box; uint32_t ref; Cone cone; };
+    // the slots the subtree under (box, ref, cone) occupies when it is given k of them
+    void spread(const Slot& s, int k, std::vector<Slot>& slots) const {
+        if ((s.ref & IREF_LEAF) || k == 1 || plan[s.ref].left[k - 1] == 0) { slots.push_back(s); return; }
+        const Bin& b = tmp[s.ref];
+        // find the k' <= k the plan actually used (share[k] may have been inherited from k - 1)
+        int i = plan[s.ref].left[k - 1];
+        int j = k - i;
+        spread(Slot{b.box[0], b.ref[0], b.cone[0]}, i, slots);
+        spread(Slot{b.box[1], b.ref[1], b.cone[1]}, j, slots);
+    }
+
+    // Emits the wide node of binary node `b` (and, recursively, of every slot that stays an inner node).
     uint32_t emit(uint32_t b, uint32_t depth) {
         wide_depth = std::max(wide_depth, depth);
-        struct Slot { Aabb box; uint32_t ref; Cone cone; };
-        // how often a random ray enters the slot: surface of the box * fraction of directions inside its cone
-        auto entered = [](const Slot& sl) { return surface(sl.box) * (sl.cone.open() ? 1.f : (float)(1.0 - std::cos(sl.cone.alpha))); };
-        std::vector<Slot> slots = {{tmp[b].box[0], tmp[b].ref[0], tmp[b].cone[0]}, {tmp[b].box[1], tmp[b].ref[1], tmp[b].cone[1]}};
-        while (slots.size() < 4) {
-            int pick = -1;
-            float area = -1.f;
-            for (size_t i = 0; i < slots.size(); ++i)
-                if (!(slots[i].ref & IREF_LEAF) && entered(slots[i]) > area) { area = entered(slots[i]); pick = (int)i; }
-            if (pick < 0) break;
-            const Bin& c = tmp[slots[pick].ref];
-            slots[pick] = Slot{c.box[0], c.ref[0], c.cone[0]};
-            slots.push_back(Slot{c.box[1], c.ref[1], c.cone[1]});
+        if (plan.empty()) make_plan();
+        std::vector<Slot> slots;
+        {
+            // the node's own 4 slots: the best split between its two children
+            const Bin& bn = tmp[b];
+            int best_i = 1;
+            float best = 3.0e38f;
+            for (int k = 2; k <= 4; ++k)
+                for (int i = 1; i < k; ++i) {
+                    float c = plan_cost(bn.ref[0], i) + plan_cost(bn.ref[1], k - i);
+                    if (c < best) { best = c; best_i = i | ((k - i) << 4); }
+                }
+            spread(Slot{bn.box[0], bn.ref[0], bn.cone[0]}, best_i & 15, slots);
+            spread(Slot{bn.box[1], bn.ref[1], bn.cone[1]}, best_i >> 4, slots);
         }
         uint32_t me = (uint32_t)(out.size() / kIndexNodeF4);
         out.resize(out.size() + kIndexNodeF4, f4{0, 0, 0, 0});

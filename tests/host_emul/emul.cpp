@@ -14,6 +14,8 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -160,5 +162,48 @@ int emu_shade_parts(void* h, uint32_t feat, long n, const float* x, const float*
     else if (feat == FE_ALL) shade_parts<FE_ALL>(S, n, x, nr, seed, dir, pdf, prim, o, d, tn);
     else return -1;
     return 0;
+}
+
+// ---- development probe: where the index traversal spends its node visits.  Per node HEIGHT (0 = all children are
+//      leaves): visits, children whose box test passed, children that also passed the cone test, per call.
+int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t* out /* [32][3] */) {
+    EmuScene* e = (EmuScene*)h;
+    const DevScene& S = e->dev;
+    const FlatScene& F = e->host.flat;
+    const size_t nn = F.inodes.size() / kIndexNodeF4;
+    std::vector<int> height(nn, -1);
+    // children are emitted after their parent: a reverse sweep sees them first
+    for (size_t i = nn; i-- > 0;) {
+        const uint32_t* w = (const uint32_t*)&F.inodes[kIndexNodeF4 * i];
+        int hh = 0;
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r = w[12 + c];
+            if (r == IREF_NONE || (r & IREF_LEAF)) continue;
+            hh = std::max(hh, height[r] + 1);
+        }
+        height[i] = hh;
+    }
+    for (int i = 0; i < 32 * 3; ++i) out[i] = 0;
+    if (S.iroot == IREF_NONE || (S.iroot & IREF_LEAF)) return 0;
+    for (long i = 0; i < n; ++i) {
+        vec3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        vec3 inv = ray_inv(rd), oi = ro * inv;
+        ConeDir dn = cone_dir(rd), none = dn;
+        none.xy = 0x7E007E00u; none.zz = 0x7E007E00u;  // NaN halves: nothing is culled by the cones
+        std::vector<uint32_t> st{S.iroot};
+        while (!st.empty()) {
+            uint32_t node = st.back();
+            st.pop_back();
+            NodeVisit box = index_visit(S, node, inv, oi, none), both = index_visit(S, node, inv, oi, dn);
+            int hh = std::min(height[node], 31);
+            out[3 * hh] += 1;
+            for (int c = 0; c < 4; ++c) {
+                out[3 * hh + 1] += box.hit[c];
+                out[3 * hh + 2] += both.hit[c];
+                if (both.hit[c] && !(both.ref[c] & IREF_LEAF)) st.push_back(both.ref[c]);
+            }
+        }
+    }
+    return (int)nn;
 }
 }

@@ -206,4 +206,65 @@ int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t*
     }
     return (int)nn;
 }
+
+// ---- structure of the index tree: out = {nodes, leaf slots, leaf slots seen twice, units missing, nodes with fewer
+//      than 2 used slots (other than the root), child boxes (fp16, as the device decodes them) that fail to contain
+//      the exact box of a reference leaf below them, deepest level}
+int emu_index_check(void* h, uint64_t* out /* [7] */) {
+    EmuScene* e = (EmuScene*)h;
+    const DevScene& S = e->dev;
+    const FlatScene& F = e->host.flat;
+    for (int i = 0; i < 7; ++i) out[i] = 0;
+    const size_t nn = F.inodes.size() / kIndexNodeF4;
+    out[0] = nn;
+    if (S.iroot == IREF_NONE || (S.iroot & IREF_LEAF)) return 0;
+    std::vector<uint8_t> seen(e->host.prims.size(), 0);
+    struct Item { uint32_t node; int depth; float mn[3], mx[3]; bool bounded; };
+    std::vector<Item> st;
+    st.push_back(Item{S.iroot, 1, {0, 0, 0}, {0, 0, 0}, false});
+    while (!st.empty()) {
+        Item it = st.back();
+        st.pop_back();
+        out[6] = std::max<uint64_t>(out[6], (uint64_t)it.depth);
+        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)it.node;
+        const float4 q0 = nd[0], q1 = nd[1], q2 = nd[2], q3 = nd[3];
+        float2 cx[2] = {unpack_half2(q0.x), unpack_half2(q0.y)}, cy[2] = {unpack_half2(q0.z), unpack_half2(q0.w)};
+        float2 cz[2] = {unpack_half2(q1.x), unpack_half2(q1.y)}, hx[2] = {unpack_half2(q1.z), unpack_half2(q1.w)};
+        float2 hy[2] = {unpack_half2(q2.x), unpack_half2(q2.y)}, hz[2] = {unpack_half2(q2.z), unpack_half2(q2.w)};
+        uint32_t refs[4] = {__float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z), __float_as_uint(q3.w)};
+        int used = 0;
+        for (int c = 0; c < 4; ++c) {
+            if (refs[c] == IREF_NONE) continue;
+            ++used;
+            auto pick = [&](float2* a) { return (c & 1) ? a[c >> 1].y : a[c >> 1].x; };
+            float C[3] = {pick(cx), pick(cy), pick(cz)}, H[3] = {pick(hx), pick(hy), pick(hz)};
+            Item ch{0, it.depth + 1, {C[0] - H[0], C[1] - H[1], C[2] - H[2]}, {C[0] + H[0], C[1] + H[1], C[2] + H[2]}, true};
+            if (it.bounded)  // a child also lies inside everything above it
+                for (int a = 0; a < 3; ++a) { ch.mn[a] = std::max(ch.mn[a], it.mn[a]); ch.mx[a] = std::min(ch.mx[a], it.mx[a]); }
+            if (refs[c] & IREF_LEAF) {
+                ++out[1];
+                uint32_t first = refs[c] & 0xFFFFFFu;
+                if (first >= seen.size()) { ++out[3]; continue; }
+                if (seen[first]) ++out[2];
+                seen[first] = 1;
+                const f4 bmn = F.ubox[2 * (size_t)first], bmx = F.ubox[2 * (size_t)first + 1];
+                const float emn[3] = {bmn.x, bmn.y, bmn.z}, emx[3] = {bmx.x, bmx.y, bmx.z};
+                for (int a = 0; a < 3; ++a)
+                    if (!(ch.mn[a] <= emn[a] && emx[a] <= ch.mx[a])) { ++out[5]; break; }
+            } else {
+                ch.node = refs[c];
+                st.push_back(ch);
+            }
+        }
+        if (used < 2 && it.node != S.iroot) ++out[4];
+    }
+    // every reference leaf (unit) must have been reached: units are the leaves of the reference tree
+    uint64_t units = 0;
+    for (size_t v = 0; v < e->host.nodes.size(); ++v)
+        if (e->host.nodes[v].left == UINT32_MAX && e->host.nodes[v].count > 0) {
+            ++units;
+            if (!seen[e->host.nodes[v].first]) ++out[3];
+        }
+    return (int)units;
+}
 }

@@ -38,6 +38,7 @@ def emu():
     L.emu_scene_parse_dialect.restype = C.c_void_p
     L.emu_scene_parse_dialect.argtypes = [C.c_char_p, C.c_long, C.c_int]
     L.emu_frame_linear.argtypes = [C.c_void_p, f32p]
+    L.emu_index_check.argtypes = [C.c_void_p, u64p]
     L.emu_scene_features.restype = C.c_uint32
     L.emu_scene_features.argtypes = [C.c_void_p]
     L.emu_shade_parts.argtypes = [C.c_void_p, C.c_uint32, C.c_long, f32p, f32p, C.c_uint32, f32p, f32p, i32p, f32p, f32p, f32p]
@@ -256,3 +257,22 @@ def test_feasibility_cones_never_cull_a_hit(emu, case):
         if need_hits:
             assert (b[0] >= 0).mean() > 0.5, (case, (b[0] >= 0).mean())
     emu.emu_scene_free(h)
+
+
+@pytest.mark.parametrize("name", ["practice5_1", "practice5_2", "lights_mix", "rabbid", "practice5_dragon_10k", "practice5_dragon_100k"])
+def test_index_tree_structure(emu, name):
+    """The collapsed 4-wide index tree: every reference leaf sits in exactly one slot, no inner node wastes a visit
+    on a single child, and every fp16 child box (as the device decodes it, intersected with the boxes above it)
+    contains the exact boxes of the reference leaves below it -- the index may only ADD candidates."""
+    h = emu.emu_scene_load(scene_path(name).encode())
+    out = np.zeros(7, np.uint64)
+    units = emu.emu_index_check(h, out)
+    emu.emu_scene_free(h)
+    nodes, leaf_slots, twice, missing, thin, uncovered, depth = [int(v) for v in out]
+    if units <= 1:
+        assert nodes == 0
+        return
+    assert leaf_slots == units and twice == 0 and missing == 0
+    assert thin == 0
+    assert uncovered == 0
+    assert nodes <= units - 1 and depth <= 40

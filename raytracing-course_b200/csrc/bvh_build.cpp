@@ -335,11 +335,12 @@ struct IndexBuilder {
     // Visiting a wide node costs the same whatever it holds, so the quantity to minimise is the expected number of
     // wide nodes a random ray enters: sum over wide nodes of P(enter) = surface of its box * fraction of directions
     // inside its cone.  best[n][k-1] = least such sum for the subtree of binary node n when it may occupy at most k
-    // slots of its parent's wide node: either one slot (n becomes a wide node itself: P(n) + its own best use of 4
+    // slots of its parent's wide node: either one slot (n becomes a wide node itself: P(n) + its own best use of W
     // slots), or the slots are shared between its two children.  A leaf costs nothing in any number of slots.
+    static constexpr int W = (int)kNodeWidth;
     struct Plan {
-        float cost[4];
-        uint8_t left[4];  // slots given to the left child when the subtree is spread over k slots; 0 = "n is one wide node"
+        float cost[W];
+        uint8_t left[W];  // slots given to the left child when the subtree is spread over k slots; 0 = "n is one wide node"
     };
     std::vector<Plan> plan;
     float entered(const Aabb& box, const Cone& cone) const {
@@ -352,9 +353,9 @@ struct IndexBuilder {
         for (size_t n = tmp.size(); n-- > 0;) {
             const Bin& b = tmp[n];
             Plan& p = plan[n];
-            float share[5];      // share[k] = least cost of spreading n's two children over exactly k >= 2 slots
-            uint8_t share_left[5];
-            for (int k = 2; k <= 4; ++k) {
+            float share[W + 1];      // share[k] = least cost of spreading n's two children over at most k >= 2 slots
+            uint8_t share_left[W + 1];
+            for (int k = 2; k <= W; ++k) {
                 share[k] = 3.0e38f; share_left[k] = 1;
                 for (int i = 1; i < k; ++i) {
                     float c = plan_cost(b.ref[0], i) + plan_cost(b.ref[1], k - i);
@@ -364,10 +365,10 @@ struct IndexBuilder {
             }
             Aabb whole = b.box[0];
             grow(whole, b.box[1]);
-            float self = entered(whole, merge_cones(b.cone[0], b.cone[1])) + share[4];
+            float self = entered(whole, merge_cones(b.cone[0], b.cone[1])) + share[W];
             if (!(self < 3.0e38f)) self = 3.0e38f;
             p.cost[0] = self; p.left[0] = 0;
-            for (int k = 2; k <= 4; ++k) {
+            for (int k = 2; k <= W; ++k) {
                 if (share[k] < self) { p.cost[k - 1] = share[k]; p.left[k - 1] = share_left[k]; }
                 else { p.cost[k - 1] = self; p.left[k - 1] = 0; }
             }
@@ -391,11 +392,11 @@ struct IndexBuilder {
         if (plan.empty()) make_plan();
         std::vector<Slot> slots;
         {
-            // the node's own 4 slots: the best split between its two children
+            // the node's own W slots: the best split between its two children
             const Bin& bn = tmp[b];
-            int best_i = 1;
+            int best_i = 1 | (1 << 4);
             float best = 3.0e38f;
-            for (int k = 2; k <= 4; ++k)
+            for (int k = 2; k <= W; ++k)
                 for (int i = 1; i < k; ++i) {
                     float c = plan_cost(bn.ref[0], i) + plan_cost(bn.ref[1], k - i);
                     if (c < best) { best = c; best_i = i | ((k - i) << 4); }
@@ -405,66 +406,70 @@ struct IndexBuilder {
         }
         uint32_t me = (uint32_t)(out.size() / kIndexNodeF4);
         out.resize(out.size() + kIndexNodeF4, f4{0, 0, 0, 0});
-        uint16_t hv[6][4];
-        uint16_t cv[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // axis x, y, z, threshold; all 0 = never culled
-        uint32_t refs[4];
-        for (int i = 0; i < 4; ++i) {
-            bool used = i < (int)slots.size();
-            // unused slot: a far-away point box and the IREF_NONE marker
-            Aabb bx = used ? slots[i].box : Aabb{{60000.f, 60000.f, 60000.f}, {60000.f, 60000.f, 60000.f}};
+        // one block of 4 children after the other (a node of width 8 is two blocks of the same layout)
+        for (int blk = 0; blk < W / 4; ++blk) {
+            uint16_t hv[6][4];
+            uint16_t cv[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // axis x, y, z, threshold; all 0 = never culled
+            uint32_t refs[4];
+            for (int i = 0; i < 4; ++i) {
+                const int si = 4 * blk + i;  // slot of the node = child i of block blk
+                bool used = si < (int)slots.size();
+                // unused slot: a far-away point box and the IREF_NONE marker
+                Aabb bx = used ? slots[si].box : Aabb{{60000.f, 60000.f, 60000.f}, {60000.f, 60000.f, 60000.f}};
 #if RTC_NODE_CENTRE_HALF
-            // centre rounded to the nearest half, half-extent rounded UP so that [c - h, c + h] covers the box
-            const float mn[3] = {bx.mn.x, bx.mn.y, bx.mn.z}, mx[3] = {bx.mx.x, bx.mx.y, bx.mx.z};
-            for (int a = 0; a < 3; ++a) {
-                uint16_t c16 = half_bits_rn(0.5f * (mn[a] + mx[a]));
-                double c = (double)half_to_float(c16);
-                // + slack: the device evaluates fma(c, 1/d, -(o * 1/d)) -+ h |1/d|, whose rounding is a few ulp of
-                // |o / d| and |c / d|, i.e. a few 2^-24 of the scene size in world units; the child boxes must stay
-                // conservative even when a face is exactly representable in fp16 (no rounding margin of its own)
-                double need = std::max((double)mx[a] - c, c - (double)mn[a]) + slack;
-                float nf = (float)need;
-                if ((double)nf < need) nf = std::nextafter(nf, INFINITY);
-                hv[a][i] = c16;
-                hv[3 + a][i] = half_up(nf);
-                if ((c16 & 0x7C00u) == 0x7C00u || !(need <= 65504.0)) { hv[a][i] = 0; hv[3 + a][i] = 0x7C00u; }  // beyond fp16: always visited
-            }
-#else
-            hv[0][i] = half_down(bx.mn.x); hv[1][i] = half_down(bx.mn.y); hv[2][i] = half_down(bx.mn.z);
-            hv[3][i] = half_up(bx.mx.x); hv[4][i] = half_up(bx.mx.y); hv[5][i] = half_up(bx.mx.z);
-#endif
-            if (used && !slots[i].cone.open()) {
-                // The device culls the child when |dn . axis| < threshold, dn = normalised ray direction, all in
-                // half precision: the axis components round to nearest (error <= 8.7e-4 in the dot product), dn
-                // likewise, three half products / sums add <= 2.5e-3; the threshold gives 8e-3 away and is
-                // rounded down.  A threshold that ends up <= 0 leaves the child unrestricted.
-                const Cone& c = slots[i].cone;
-                const double thr = std::cos(std::min(c.alpha + 2e-3, 1.5707963)) - 8e-3;
-                if (thr > 0) {
-                    cv[0][i] = half_bits_rn((float)c.ax); cv[1][i] = half_bits_rn((float)c.ay); cv[2][i] = half_bits_rn((float)c.az);
-                    cv[3][i] = half_down((float)thr);
-                    if (cv[3][i] & 0x8000u) cv[3][i] = 0;
+                // centre rounded to the nearest half, half-extent rounded UP so that [c - h, c + h] covers the box
+                const float mn[3] = {bx.mn.x, bx.mn.y, bx.mn.z}, mx[3] = {bx.mx.x, bx.mx.y, bx.mx.z};
+                for (int a = 0; a < 3; ++a) {
+                    uint16_t c16 = half_bits_rn(0.5f * (mn[a] + mx[a]));
+                    double c = (double)half_to_float(c16);
+                    // + slack: the device evaluates fma(c, 1/d, -(o * 1/d)) -+ h |1/d|, whose rounding is a few ulp of
+                    // |o / d| and |c / d|, i.e. a few 2^-24 of the scene size in world units; the child boxes must stay
+                    // conservative even when a face is exactly representable in fp16 (no rounding margin of its own)
+                    double need = std::max((double)mx[a] - c, c - (double)mn[a]) + slack;
+                    float nf = (float)need;
+                    if ((double)nf < need) nf = std::nextafter(nf, INFINITY);
+                    hv[a][i] = c16;
+                    hv[3 + a][i] = half_up(nf);
+                    if ((c16 & 0x7C00u) == 0x7C00u || !(need <= 65504.0)) { hv[a][i] = 0; hv[3 + a][i] = 0x7C00u; }  // beyond fp16: always visited
                 }
-            }
-            refs[i] = IREF_NONE;
-            if (used) refs[i] = (slots[i].ref & IREF_LEAF) ? slots[i].ref : emit(slots[i].ref, depth + 1);
-        }
-        uint32_t w[16];
-        for (int r = 0; r < 6; ++r) {
-            w[2 * r] = (uint32_t)hv[r][0] | ((uint32_t)hv[r][1] << 16);
-            w[2 * r + 1] = (uint32_t)hv[r][2] | ((uint32_t)hv[r][3] << 16);
-        }
-        for (int i = 0; i < 4; ++i) w[12 + i] = refs[i];
-        for (int q = 0; q < 4; ++q) out[kIndexNodeF4 * me + q] = bits4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-#if RTC_NODE_CONES
-        // q4 = axis.x[0..3] axis.y[0..3] ; q5 = axis.z[0..3] threshold[0..3]  (halves, two children per word)
-        uint32_t cw[8];
-        for (int r = 0; r < 4; ++r) {
-            cw[2 * r] = (uint32_t)cv[r][0] | ((uint32_t)cv[r][1] << 16);
-            cw[2 * r + 1] = (uint32_t)cv[r][2] | ((uint32_t)cv[r][3] << 16);
-        }
-        out[kIndexNodeF4 * me + 4] = bits4(cw[0], cw[1], cw[2], cw[3]);
-        out[kIndexNodeF4 * me + 5] = bits4(cw[4], cw[5], cw[6], cw[7]);
+#else
+                hv[0][i] = half_down(bx.mn.x); hv[1][i] = half_down(bx.mn.y); hv[2][i] = half_down(bx.mn.z);
+                hv[3][i] = half_up(bx.mx.x); hv[4][i] = half_up(bx.mx.y); hv[5][i] = half_up(bx.mx.z);
 #endif
+                if (used && !slots[si].cone.open()) {
+                    // The device culls the child when |dn . axis| < threshold, dn = normalised ray direction, all in
+                    // half precision: the axis components round to nearest (error <= 8.7e-4 in the dot product), dn
+                    // likewise, three half products / sums add <= 2.5e-3; the threshold gives 8e-3 away and is
+                    // rounded down.  A threshold that ends up <= 0 leaves the child unrestricted.
+                    const Cone& c = slots[si].cone;
+                    const double thr = std::cos(std::min(c.alpha + 2e-3, 1.5707963)) - 8e-3;
+                    if (thr > 0) {
+                        cv[0][i] = half_bits_rn((float)c.ax); cv[1][i] = half_bits_rn((float)c.ay); cv[2][i] = half_bits_rn((float)c.az);
+                        cv[3][i] = half_down((float)thr);
+                        if (cv[3][i] & 0x8000u) cv[3][i] = 0;
+                    }
+                }
+                refs[i] = IREF_NONE;
+                if (used) refs[i] = (slots[si].ref & IREF_LEAF) ? slots[si].ref : emit(slots[si].ref, depth + 1);
+            }
+            uint32_t w[16];
+            for (int r = 0; r < 6; ++r) {
+                w[2 * r] = (uint32_t)hv[r][0] | ((uint32_t)hv[r][1] << 16);
+                w[2 * r + 1] = (uint32_t)hv[r][2] | ((uint32_t)hv[r][3] << 16);
+            }
+            for (int i = 0; i < 4; ++i) w[12 + i] = refs[i];
+            for (int q = 0; q < 4; ++q) out[kIndexNodeF4 * me + kIndexBlockF4 * blk + q] = bits4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+#if RTC_NODE_CONES
+            // q4 = axis.x[0..3] axis.y[0..3] ; q5 = axis.z[0..3] threshold[0..3]  (halves, two children per word)
+            uint32_t cw[8];
+            for (int r = 0; r < 4; ++r) {
+                cw[2 * r] = (uint32_t)cv[r][0] | ((uint32_t)cv[r][1] << 16);
+                cw[2 * r + 1] = (uint32_t)cv[r][2] | ((uint32_t)cv[r][3] << 16);
+            }
+            out[kIndexNodeF4 * me + kIndexBlockF4 * blk + 4] = bits4(cw[0], cw[1], cw[2], cw[3]);
+            out[kIndexNodeF4 * me + kIndexBlockF4 * blk + 5] = bits4(cw[4], cw[5], cw[6], cw[7]);
+#endif
+        }
         return me;
     }
 };

@@ -418,8 +418,8 @@ RT_D vec3 ray_inv(vec3 d) {
     return mk3(fminf(fmaxf(1.0f / d.x, -big), big), fminf(fmaxf(1.0f / d.y, -big), big), fminf(fmaxf(1.0f / d.z, -big), big));
 }
 struct NodeVisit {
-    uint32_t ref[4];
-    bool hit[4];
+    uint32_t ref[kNodeWidth];
+    bool hit[kNodeWidth];
 };
 RT_D void slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 inv, vec3 oi, uint32_t ref, bool& hit, float& tc) {
     float x1 = fmaf(mnx, inv.x, -oi.x), x2 = fmaf(mxx, inv.x, -oi.x);
@@ -500,8 +500,8 @@ RT_D uint32_t cone_cull_pair(ConeDir dn, float wx, float wy, float wz, float wt)
     return (fabsf(d0) < th.x ? 1u : 0u) | (fabsf(d1) < th.y ? 0x10000u : 0u);
 #endif
 }
-RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi, ConeDir dn) {
-    const float4* nd = S.inodes + kIndexNodeF4 * (size_t)node;
+// one block of 4 children: boxes, refs, cones (ref / hit point at the block's 4 entries of the NodeVisit)
+RT_D void index_visit_block(const float4* nd, vec3 inv, vec3 oi, ConeDir dn, uint32_t* ref, bool* hit) {
     float4 q0, q1, q2, q3;
     ldg8(nd, q0, q1);
     ldg8(nd + 2, q2, q3);
@@ -510,30 +510,35 @@ RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi, 
     const float2 ax01 = unpack_half2(q0.x), ax23 = unpack_half2(q0.y), ay01 = unpack_half2(q0.z), ay23 = unpack_half2(q0.w);
     const float2 az01 = unpack_half2(q1.x), az23 = unpack_half2(q1.y), bx01 = unpack_half2(q1.z), bx23 = unpack_half2(q1.w);
     const float2 by01 = unpack_half2(q2.x), by23 = unpack_half2(q2.y), bz01 = unpack_half2(q2.z), bz23 = unpack_half2(q2.w);
-    NodeVisit v;
-    v.ref[0] = __float_as_uint(q3.x); v.ref[1] = __float_as_uint(q3.y);
-    v.ref[2] = __float_as_uint(q3.z); v.ref[3] = __float_as_uint(q3.w);
+    ref[0] = __float_as_uint(q3.x); ref[1] = __float_as_uint(q3.y);
+    ref[2] = __float_as_uint(q3.z); ref[3] = __float_as_uint(q3.w);
 #if RTC_NODE_CENTRE_HALF
-    slab_ch(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, v.ref[0], v.hit[0]);
-    slab_ch(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, v.ref[1], v.hit[1]);
-    slab_ch(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, v.ref[2], v.hit[2]);
-    slab_ch(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, v.ref[3], v.hit[3]);
+    slab_ch(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, ref[0], hit[0]);
+    slab_ch(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, ref[1], hit[1]);
+    slab_ch(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, ref[2], hit[2]);
+    slab_ch(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, ref[3], hit[3]);
 #else
     float tc;
-    slab(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, v.ref[0], v.hit[0], tc);
-    slab(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, v.ref[1], v.hit[1], tc);
-    slab(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, v.ref[2], v.hit[2], tc);
-    slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, v.ref[3], v.hit[3], tc);
+    slab(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, ref[0], hit[0], tc);
+    slab(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, ref[1], hit[1], tc);
+    slab(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, ref[2], hit[2], tc);
+    slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, ref[3], hit[3], tc);
 #endif
 #if RTC_NODE_CONES
     float4 q4, q5;
     ldg8(nd + 4, q4, q5);  // axis.x[0..3] axis.y[0..3] | axis.z[0..3] threshold[0..3]
     const uint32_t c01 = cone_cull_pair(dn, q4.x, q4.z, q5.x, q5.z), c23 = cone_cull_pair(dn, q4.y, q4.w, q5.y, q5.w);
-    v.hit[0] = v.hit[0] && !(c01 & 1u); v.hit[1] = v.hit[1] && !(c01 >> 16);
-    v.hit[2] = v.hit[2] && !(c23 & 1u); v.hit[3] = v.hit[3] && !(c23 >> 16);
+    hit[0] = hit[0] && !(c01 & 1u); hit[1] = hit[1] && !(c01 >> 16);
+    hit[2] = hit[2] && !(c23 & 1u); hit[3] = hit[3] && !(c23 >> 16);
 #else
     (void)dn;
 #endif
+}
+RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi, ConeDir dn) {
+    const float4* nd = S.inodes + kIndexNodeF4 * (size_t)node;
+    NodeVisit v;
+#pragma unroll
+    for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) index_visit_block(nd + kIndexBlockF4 * blk, inv, oi, dn, v.ref + 4 * blk, v.hit + 4 * blk);
     return v;
 }
 // closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)
@@ -646,7 +651,7 @@ RT_D bool collect_leaf_hits(const DevScene& S, vec3 o, vec3 d, LeafRec* rec, int
         NodeVisit v = index_visit(S, ref, inv, oi, dn);
         bool have = false;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < (int)kNodeWidth; ++c) {
             if (!v.hit[c]) continue;
             if (!have) { ref = v.ref[c]; have = true; continue; }
             if (sp + 1 > kIndexStack) return false;

@@ -45,7 +45,14 @@ RT_D bool pre_step(const DevScene& S, vec3 o, vec3 d, float& cd, uint32_t& id) {
     }
     vec3 inv = ray_inv(d);
     NodeVisit v = index_visit(S, S.iroot, inv, o * inv, cone_dir(d));
+#if RTC_NODE_WIDTH == 4
     return v.hit[0] || v.hit[1] || v.hit[2] || v.hit[3];
+#else
+    bool any = false;
+#pragma unroll
+    for (uint32_t c = 0; c < kNodeWidth; ++c) any = any || v.hit[c];
+    return any;
+#endif
 }
 // warp-aggregated append of slot `i` to the traverse queue; call with the full warp converged
 RT_D void enqueue(bool enters, uint32_t i, uint32_t* tq, uint32_t* tq_count, uint32_t lane) {
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
 
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
-        const bool room = sp + nl + 7 <= kStackWords;
+        const bool room = sp + nl + (2 * (int)kNodeWidth - 1) <= kStackWords;  // a visit notes up to W leaves and pushes up to W - 1 nodes
 #if !RTC_LAZY_OVERFLOW
         if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
 #endif
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 const uint32_t top = stk[spm];
                 uint32_t next = kNone;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < (int)kNodeWidth; ++c) {
                     const bool leaf = (v.ref[c] & IREF_LEAF) != 0;
                     if (v.hit[c] && leaf) {  // note the leaf, test it later
                         ++nl;

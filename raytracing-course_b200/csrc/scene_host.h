@@ -142,7 +142,16 @@ constexpr uint32_t IREF_NONE = 0xFFFFFFFFu;
 constexpr uint32_t IREF_FAST = 0x40000000u;     // leaf = one triangle with pos 0 and identity rotation
 constexpr uint32_t IREF_MAX_LEAF_PRIMS = 64;   // 6 bits (24..29)
 constexpr uint32_t IREF_MAX_PRIMS = 1u << 24;
-constexpr uint32_t kIndexNodeF4 = RTC_NODE_CONES ? 6 : 4;  // float4 per index node
+// Children per index node: 4, or 8 = two 4-child blocks of the same layout fetched by ONE visit (the collapse
+// predicts 35 % fewer entered nodes at 8: profiles/r01_experiments.md; prepared for an A/B run, 4 is the measured
+// default).
+#ifndef RTC_NODE_WIDTH
+#define RTC_NODE_WIDTH 4
+#endif
+static_assert(RTC_NODE_WIDTH == 4 || RTC_NODE_WIDTH == 8, "index nodes hold 4 or 8 children");
+constexpr uint32_t kNodeWidth = RTC_NODE_WIDTH;
+constexpr uint32_t kIndexBlockF4 = RTC_NODE_CONES ? 6 : 4;                  // float4 per block of 4 children
+constexpr uint32_t kIndexNodeF4 = kIndexBlockF4 * (kNodeWidth / 4);          // float4 per index node
 
 Aabb aabb_of_primitive(const Primitive& p);  // AABB_t::AABB_t(const Primitive&) src/bvh.cpp:41-87
 

@@ -174,10 +174,10 @@ int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t*
     std::vector<int> height(nn, -1);
     // children are emitted after their parent: a reverse sweep sees them first
     for (size_t i = nn; i-- > 0;) {
-        const uint32_t* w = (const uint32_t*)&F.inodes[kIndexNodeF4 * i];
         int hh = 0;
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r = w[12 + c];
+        for (int c = 0; c < (int)kNodeWidth; ++c) {
+            const uint32_t* w = (const uint32_t*)&F.inodes[kIndexNodeF4 * i + kIndexBlockF4 * (c / 4)];
+            uint32_t r = w[12 + (c & 3)];
             if (r == IREF_NONE || (r & IREF_LEAF)) continue;
             hh = std::max(hh, height[r] + 1);
         }
@@ -197,7 +197,7 @@ int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t*
             NodeVisit box = index_visit(S, node, inv, oi, none), both = index_visit(S, node, inv, oi, dn);
             int hh = std::min(height[node], 31);
             out[3 * hh] += 1;
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < (int)kNodeWidth; ++c) {
                 out[3 * hh + 1] += box.hit[c];
                 out[3 * hh + 2] += both.hit[c];
                 if (both.hit[c] && !(both.ref[c] & IREF_LEAF)) st.push_back(both.ref[c]);
@@ -226,13 +226,14 @@ int emu_index_check(void* h, uint64_t* out /* [7] */) {
         Item it = st.back();
         st.pop_back();
         out[6] = std::max<uint64_t>(out[6], (uint64_t)it.depth);
-        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)it.node;
+        int used = 0;
+        for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) {
+        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)it.node + kIndexBlockF4 * blk;
         const float4 q0 = nd[0], q1 = nd[1], q2 = nd[2], q3 = nd[3];
         float2 cx[2] = {unpack_half2(q0.x), unpack_half2(q0.y)}, cy[2] = {unpack_half2(q0.z), unpack_half2(q0.w)};
         float2 cz[2] = {unpack_half2(q1.x), unpack_half2(q1.y)}, hx[2] = {unpack_half2(q1.z), unpack_half2(q1.w)};
         float2 hy[2] = {unpack_half2(q2.x), unpack_half2(q2.y)}, hz[2] = {unpack_half2(q2.z), unpack_half2(q2.w)};
         uint32_t refs[4] = {__float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z), __float_as_uint(q3.w)};
-        int used = 0;
         for (int c = 0; c < 4; ++c) {
             if (refs[c] == IREF_NONE) continue;
             ++used;
@@ -255,6 +256,7 @@ int emu_index_check(void* h, uint64_t* out /* [7] */) {
                 ch.node = refs[c];
                 st.push_back(ch);
             }
+        }
         }
         if (used < 2 && it.node != S.iroot) ++out[4];
     }

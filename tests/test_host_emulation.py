@@ -27,9 +27,15 @@ def emu():
     cuda_inc = "/usr/local/cuda/include"
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
-    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in srcs + objs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
-                               "-I" + cuda_inc, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+    # RTC_EMU_DEFS="-DRTC_NODE_WIDTH=8" (or any other build-time switch of the product) runs this whole file against
+    # that configuration: the host sources are then compiled with the same defines instead of taking the built objects
+    defs = os.environ.get("RTC_EMU_DEFS", "").split()
+    if defs:
+        so = os.path.join(EMU_DIR, "libemul_variant.so")
+        objs = [os.path.join(CSRC, "scene_load.cpp"), os.path.join(CSRC, "bvh_build.cpp")]
+    if defs or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in srcs + objs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off"] + defs +
+                              ["-I" + cuda_inc, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
                                srcs[0]] + objs + ["-o", so])
     L = C.CDLL(so)
     L.emu_scene_load.restype = C.c_void_p

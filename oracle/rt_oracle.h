@@ -32,8 +32,9 @@ void orc_scene_free(orc_scene* s);
    Scene::RayTrace: 1 ray casting in double, 2 Whitted with point / directional lights, 3 path tracing with
    uniform-hemisphere sampling, 4 = hw5's estimator without triangles and BVH.  orc_render_sum on a dialect 1 / 2
    scene returns the deterministic frame (linear colour, once).  Pinned by tests/golden/hw*_*.npz (images of the
-   compiled reference programs); known deviation: primitives are rotated with glm's float quaternion-vector
-   product as in hw4/hw5, hw1..hw3 use a double-precision sandwich product (identical for unit quaternions). */
+   compiled reference programs); known deviation: hw2 / hw3 primitives are rotated with glm's float quaternion-vector
+   product as in hw4/hw5, the snapshots themselves use the sandwich product q v q* (identical for unit quaternions,
+   scaled by |q|^2 otherwise); hw1 is restated in double with its own sandwich product. */
 orc_scene* orc_scene_load_dialect(const char* path, int dialect);
 orc_scene* orc_scene_parse_dialect(const char* text, long len, int dialect);
 int orc_scene_dialect(const orc_scene* s);

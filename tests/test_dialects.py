@@ -15,6 +15,9 @@ import orclib
 from conftest import ROOT, golden
 
 DETERMINISTIC = ["hw1_course_sample6", "hw2_hw2_lights"]
+# more deterministic fixtures, checked on the CPU only (oracle here, the host compilation of the device code in
+# test_host_emulation.py): hw2_glass = nested dielectrics, total internal reflection, a metallic wall, RAY_DEPTH 8
+DETERMINISTIC_CPU = ["hw2_hw2_glass", "hw1_course_sample3", "hw1_course_sample5"]
 MONTE_CARLO = ["hw3_course_sample6", "hw4_course_sample6", "hw3_course_sample4", "hw4_course_sample4", "hw3_course_sample3", "hw4_course_sample3"]
 
 
@@ -57,7 +60,7 @@ def check_monte_carlo_u8(a, b, fixture):
 
 
 # ---------------------------------------------------------------------------------------------- CPU: the oracle
-@pytest.mark.parametrize("fixture", DETERMINISTIC)
+@pytest.mark.parametrize("fixture", DETERMINISTIC + DETERMINISTIC_CPU)
 def test_oracle_deterministic_dialects_vs_reference_images(oracle_lib, fixture):
     text, dialect, want = load(fixture)
     s = orclib.Scene(oracle_lib, text=text, dialect=dialect)
@@ -100,7 +103,7 @@ def test_oracle_dialect_vocabulary(oracle_lib):
 def test_product_reader_speaks_the_dialects(rtc, oracle_lib):
     """The product's scene reader (csrc/scene_load.cpp) and the oracle's agree on every dialect fixture: header
     values and primitive count, without a device (device = -1)."""
-    for fixture in DETERMINISTIC + MONTE_CARLO:
+    for fixture in DETERMINISTIC + DETERMINISTIC_CPU + MONTE_CARLO:
         text, dialect, _ = load(fixture)
         a = orclib.Scene(oracle_lib, text=text, dialect=dialect)
         s = rtc.Scene(text=text, device=-1, dialect=dialect)

@@ -128,7 +128,7 @@ def test_mix_pdf_and_sample(emu, oracle_scenes, name):
     emu.emu_scene_free(h)
 
 
-@pytest.mark.parametrize("fixture", ["hw1_course_sample6", "hw2_hw2_lights"])
+@pytest.mark.parametrize("fixture", ["hw1_course_sample6", "hw2_hw2_lights", "hw2_hw2_glass", "hw1_course_sample3", "hw1_course_sample5"])
 def test_deterministic_dialects_match_reference_images(emu, oracle_lib, fixture):
     """csrc/course_device.cuh (hw1 ray casting, hw2 Whitted) compiled for the host against the image the
     UNMODIFIED hwN program wrote for the same scene text (tests/golden/hwN_*.npz)."""
@@ -150,7 +150,12 @@ def test_deterministic_dialects_match_reference_images(emu, oracle_lib, fixture)
     diff = np.abs(got.reshape(want.shape).astype(int) - want.astype(int))
     # hw1 writes scene colours as they are: exact.  hw2: float summation order of the recursion may move
     # a value across a rounding boundary (1 LSB, a handful of values).
-    if dialect == 1:
+    if fixture in ("hw1_course_sample3", "hw1_course_sample5"):
+        # Cornell boxes seen head-on: along the image diagonals two walls are hit at EXACTLY the same distance.  hw1
+        # computes in double and still tells them apart; the device's float t ties and the first wall in file order
+        # wins (256 / 481 of 262,144 pixels, all on the diagonals).
+        assert (diff.max(axis=2) > 0).mean() < 2.5e-3
+    elif dialect == 1:
         assert diff.max() == 0
     else:
         assert diff.max() <= 1 and (diff > 0).mean() < 1e-3

@@ -238,6 +238,9 @@ def dialects():
     ones converged at a reduced size."""
     dialect_fixture(1, "course_sample6")
     dialect_fixture(2, "hw2_lights")
+    dialect_fixture(2, "hw2_glass")        # nested dielectrics, total internal reflection, metallic wall, RAY_DEPTH 8
+    dialect_fixture(1, "course_sample3")
+    dialect_fixture(1, "course_sample5")
     dialect_fixture(3, "course_sample6", 103, 133, 2048)
     dialect_fixture(4, "course_sample6", 103, 133, 2048)
     dialect_fixture(3, "course_sample4", 64, 64, 4096)

@@ -242,7 +242,6 @@ static uint16_t half_up(float f) {
 
 struct IndexBuilder {
     const std::vector<Unit>& units;
-    std::vector<uint32_t> order;
     std::vector<f4>& out;  // kIndexNodeF4 f4 (96 bytes) per 4-wide node
     std::vector<float> rarea;
     uint32_t max_depth = 0;
@@ -256,38 +255,44 @@ struct IndexBuilder {
     }
     Aabb bound(uint32_t lo, uint32_t hi) const {
         Aabb b = empty_box();
-        for (uint32_t i = lo; i < hi; ++i) grow(b, units[order[i]].box);
+        for (uint32_t i = lo; i < hi; ++i) grow(b, units[sorted[0][i]].box);
         return b;
     }
-    // returns the child reference for units order[lo..hi) and the feasibility cone of that subtree
-    uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth, Cone& cone) {
-        max_depth = std::max(max_depth, depth);
-        if (hi - lo == 1) { cone = units[order[lo]].cone; return leaf_ref(units[order[lo]]); }
-        // Split cost = sum over the two sides of P(a random ray enters the side) * units in it, with
-        // P = surface of the box * fraction of directions inside the feasibility cone.  Candidate orders: the
-        // unit centres along x, y, z (keys 3..5, |axis.x|, |axis.y|, |axis.z| of the units' cones, would group
-        // faces of one orientation where the surface folds back on itself; the greedy cost never profits, and forced
-        // 2-means orientation splits below 64 .. 4096 units make it worse: profiles/r01_experiments.md).
-        constexpr int kKeys = 3;        // + |axis| of the cones as three more orders: measured, no gain (5.35 vs 5.32 visits)
-        constexpr bool kConeCost = true;  // 5.54 -> 5.32 index node visits per random ray at 100k triangles
-        auto key_of = [&](uint32_t u, int key) -> float {
-            if (key < 3) return idx(units[u].centre, key);
-            const Cone& c = units[u].cone;
-            if (c.open()) return -1.f;
-            return (float)std::fabs(key == 3 ? c.ax : key == 4 ? c.ay : c.az);
-        };
-        auto sort_by = [&](int key) {
-            std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) {
-                float ca = key_of(a, key), cb = key_of(b, key);
+    // Unit ids ordered by (centre[axis], id), one array per axis; a range [lo, hi) holds the same SET of units in all
+    // three, so a node sweeps each axis without sorting and a split only has to partition the other two arrays
+    // stably (O(n) per level instead of three sorts per node: 2.2 s -> 0.9 s for 100k units, same tree bit for bit).
+    std::vector<uint32_t> sorted[3];
+    std::vector<uint32_t> scratch;
+    std::vector<uint8_t> left_side;
+    void prepare() {
+        const uint32_t n = (uint32_t)units.size();
+        for (int axis = 0; axis < 3; ++axis) {
+            sorted[axis].resize(n);
+            std::iota(sorted[axis].begin(), sorted[axis].end(), 0u);
+            std::sort(sorted[axis].begin(), sorted[axis].end(), [&](uint32_t a, uint32_t b) {
+                float ca = idx(units[a].centre, axis), cb = idx(units[b].centre, axis);
                 return ca < cb || (ca == cb && a < b);
             });
-        };
-        auto frac = [&](const Cone& c) -> float { return (!kConeCost || c.open()) ? 1.f : (float)(1.0 - std::cos(c.alpha)); };
+        }
+        scratch.resize(n);
+        left_side.assign(n, 0);
+    }
+    // returns the child reference for the units in [lo, hi) and the feasibility cone of that subtree
+    uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth, Cone& cone) {
+        max_depth = std::max(max_depth, depth);
+        if (hi - lo == 1) { cone = units[sorted[0][lo]].cone; return leaf_ref(units[sorted[0][lo]]); }
+        // Split cost = sum over the two sides of P(a random ray enters the side) * units in it, with
+        // P = surface of the box * fraction of directions inside the feasibility cone.  Candidate orders: the
+        // unit centres along x, y, z (|axis.x|, |axis.y|, |axis.z| of the units' cones as three more orders would group
+        // faces of one orientation where the surface folds back on itself; measured: the greedy cost never profits,
+        // 5.35 vs 5.32 visits, and forced 2-means orientation splits below 64 .. 4096 units make it worse:
+        // profiles/r01_experiments.md).  The cone factor itself: 5.54 -> 5.32 index node visits per random ray.
+        auto frac = [&](const Cone& c) -> float { return c.open() ? 1.f : (float)(1.0 - std::cos(c.alpha)); };
         float best = 3.0e38f;
         int best_axis = -1;
         uint32_t best_cut = 0;
-        for (int key = 0; key < kKeys; ++key) {
-            sort_by(key);
+        for (int axis = 0; axis < 3; ++axis) {
+            const std::vector<uint32_t>& order = sorted[axis];
             Aabb r = empty_box();
             Cone rc;
             for (uint32_t i = hi - 1; i > lo; --i) {
@@ -303,14 +308,26 @@ struct IndexBuilder {
                 grow(l, u.box);
                 lc = (i == lo + 1) ? u.cone : merge_cones(lc, u.cone);
                 float c = surface(l) * frac(lc) * (i - lo) + rarea[i] * (hi - i);
-                if (c < best) { best = c; best_axis = key; best_cut = i; }
+                if (c < best) { best = c; best_axis = axis; best_cut = i; }
             }
         }
         if (best_axis < 0) {  // every candidate cost was NaN/inf (degenerate boxes): split in the middle
-            best_axis = kKeys - 1;
+            best_axis = 2;
             best_cut = lo + (hi - lo) / 2;
         }
-        if (best_axis != kKeys - 1) sort_by(best_axis);
+        // the left side is the head of the winning order; the other two orders are partitioned stably around it
+        for (uint32_t i = lo; i < best_cut; ++i) left_side[sorted[best_axis][i]] = 1;
+        for (int axis = 0; axis < 3; ++axis) {
+            if (axis == best_axis) continue;
+            std::vector<uint32_t>& order = sorted[axis];
+            uint32_t nl = lo, nr = 0;
+            for (uint32_t i = lo; i < hi; ++i) {
+                if (left_side[order[i]]) order[nl++] = order[i];
+                else scratch[nr++] = order[i];
+            }
+            std::copy(scratch.begin(), scratch.begin() + nr, order.begin() + nl);
+        }
+        for (uint32_t i = lo; i < best_cut; ++i) left_side[sorted[best_axis][i]] = 0;
         // binary node in a temporary tree; emit() collapses it to 4-wide nodes afterwards
         uint32_t me = (uint32_t)tmp.size();
         tmp.push_back(Bin{});
@@ -607,14 +624,13 @@ void HostScene::init() {
     F.inodes.clear();
     F.iroot = IREF_NONE;
     if (!units.empty()) {
-        IndexBuilder ib{units, {}, F.inodes, std::vector<float>(units.size() + 1, 0.f)};
+        IndexBuilder ib{units, F.inodes, std::vector<float>(units.size() + 1, 0.f)};
         double extent = std::max({std::fabs((double)cam.pos.x), std::fabs((double)cam.pos.y), std::fabs((double)cam.pos.z)});
         for (const Unit& u : units)
             for (float v : {u.box.mn.x, u.box.mn.y, u.box.mn.z, u.box.mx.x, u.box.mx.y, u.box.mx.z})
                 if (std::isfinite(v)) extent = std::max(extent, (double)std::fabs(v));
         ib.slack = extent * (1.0 / 1048576.0);
-        ib.order.resize(units.size());
-        std::iota(ib.order.begin(), ib.order.end(), 0u);
+        ib.prepare();
         Cone whole;
         uint32_t broot = ib.build(0, (uint32_t)units.size(), 0, whole);
         F.iroot = (broot & IREF_LEAF) ? broot : ib.emit(broot, 1);

@@ -269,4 +269,16 @@ int emu_index_check(void* h, uint64_t* out /* [7] */) {
         }
     return (int)units;
 }
+
+// FNV-1a over the bytes of the flattened index tree (and its root reference): lets a test or a developer confirm
+// that a change to the host builder left the device data byte-identical
+uint64_t emu_index_hash(void* h) {
+    EmuScene* e = (EmuScene*)h;
+    const FlatScene& F = e->host.flat;
+    uint64_t x = 1469598103934665603ull;
+    auto eat = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { x ^= b[i]; x *= 1099511628211ull; } };
+    eat(F.inodes.data(), F.inodes.size() * sizeof(f4));
+    eat(&F.iroot, sizeof F.iroot);
+    return x;
+}
 }

@@ -287,3 +287,20 @@ def test_index_tree_structure(emu, name):
     assert thin == 0
     assert uncovered == 0
     assert nodes <= units - 1 and depth <= 40
+
+
+def test_index_tree_is_pinned(emu):
+    """FNV-1a of the flattened index tree of the two dragon scenes.  The tree shape decides k_traverse's speed, which
+    is measured on the B200: a change to the host builder that is meant to be neutral (a faster build, a refactoring)
+    must leave these bytes alone; a change that is meant to alter the tree updates the values together with a new
+    measurement (profiles/)."""
+    emu.emu_index_hash.restype = C.c_uint64
+    emu.emu_index_hash.argtypes = [C.c_void_p]
+    want = {"practice5_dragon_10k": 0x3489f252dd17952d, "practice5_dragon_100k": 0x8db8c0679a8cf812}
+    if os.environ.get("RTC_EMU_DEFS"):
+        pytest.skip("pinned for the default build configuration")
+    for name, value in want.items():
+        h = emu.emu_scene_load(scene_path(name).encode())
+        got = emu.emu_index_hash(h)
+        emu.emu_scene_free(h)
+        assert got == value, (name, hex(got))

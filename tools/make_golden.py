@@ -117,6 +117,48 @@ def render_fixture(name, width, height, samples, ray_depth=-1):
     s.close()
 
 
+HW2_LIGHTS = """
+NEW_LIGHT
+LIGHT_INTENSITY 0.9 0.85 0.7
+LIGHT_DIRECTION 0.3 1 -0.4
+
+NEW_LIGHT
+LIGHT_INTENSITY 30 20 20
+LIGHT_POSITION -1 5 1
+LIGHT_ATTENUATION 1 0.2 0.3
+
+NEW_LIGHT
+LIGHT_INTENSITY 4 6 12
+LIGHT_POSITION 3 0.5 -4
+LIGHT_ATTENUATION 1 0 0.5
+"""
+
+
+def hw2_lights_text(sample6):
+    """The reference's hw3/sample6.txt turned into an hw2 scene (the reference ships no hw2 scene): no SAMPLES, an
+    ambient term, one metallic and two dielectric primitives, a directional and two point lights."""
+    out = []
+    nprim = 0
+    for line in sample6.split("\n"):
+        w = line.split()
+        if w and w[0] == "SAMPLES":
+            continue
+        if w and w[0] == "RAY_DEPTH":
+            line = "RAY_DEPTH 5"
+        out.append(line)
+        if w and w[0] == "CAMERA_FOV_X":
+            out.append("AMBIENT_LIGHT 0.15 0.15 0.2")
+        if w and w[0] == "COLOR":
+            nprim += 1
+            if nprim == 3:
+                out.append("METALLIC")
+            elif nprim == 4:
+                out += ["DIELECTRIC", "IOR 1.5"]
+            elif nprim == 7:
+                out += ["DIELECTRIC", "IOR 1.33"]
+    return "\n".join(out) + HW2_LIGHTS
+
+
 def dialect_fixture(dialect, name, width=None, height=None, samples=None):
     """Image written by the unmodified hwN program (oracle/_ref/raytracing_hwN, built by oracle/Makefile from
     /root/reference/hwN) for scenes/<name>.txt with the header lines replaced; the fixture keeps the exact scene
@@ -127,7 +169,14 @@ def dialect_fixture(dialect, name, width=None, height=None, samples=None):
     reference, hw4 src/scene.cpp:39-60 then lists such primitives as lights and samples towards them)."""
     import subprocess
     import tempfile
-    base = open(os.path.join(SCENES, name + ".txt")).read()
+    # "course_sampleN" = hwN's own sample scenes: read where they lie in the reference checkout (input data of the
+    # reference; the fixture stores the text it was rendered from, so the repository keeps no copy of the files)
+    if name == "hw2_lights":
+        base = hw2_lights_text(open(os.path.join(os.environ.get("REFERENCE_ROOT", "/root/reference"), "hw3", "sample6.txt")).read())
+    elif name.startswith("course_sample"):
+        base = open(os.path.join(os.environ.get("REFERENCE_ROOT", "/root/reference"), "hw3", name.replace("course_", "") + ".txt")).read()
+    else:
+        base = open(os.path.join(SCENES, name + ".txt")).read()
     text = orclib.with_header(base, width, height, samples)
 
     def run(scene_text):

@@ -4,8 +4,8 @@
 // under /root/reference/hw5 (nothing of the reference is copied into this repo).  It exposes
 // the reference's hot-path functions (Scene::RayIntersection, Primitive::Intersect,
 // Camera::GetToRay, Distribution::Pdf, AcesTonemap/GammaCorrected/toUInts, Scene::Sample)
-// batch-wise, so that tools/make_golden.py can record golden vectors and
-// tests/test_oracle_vs_ref.py can pin oracle/rt_oracle.c against the real thing.
+// batch-wise, so that tools/make_golden.py can record golden vectors from it and
+// tests/test_oracle_golden.py can pin oracle/rt_oracle.c against the real thing.
 // Scene's private members are reached with the usual "#define private public" test trick,
 // applied only after every standard/glm header has already been included.
 #include <algorithm>

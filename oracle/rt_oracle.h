@@ -7,7 +7,7 @@
  * may include, link or call it.  Only tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py use it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_golden.py checks every deterministic
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every deterministic
  * function below against fixtures produced by the UNMODIFIED reference compiled from
  * /root/reference (oracle/refprobe.cpp, oracle/Makefile -> oracle/_ref/), see
  * tests/golden/README.md.  The only intentional deviation is the random number

@@ -272,7 +272,8 @@ class Scene:
     def RenderSum(self, seed=0, sample_begin=0, sample_count=None):
         """Linear per-pixel radiance sums over a sample range, as an (H, W, 3) host array."""
         if sample_count is None:
-            sample_count = self.samples
+            # hw1 / hw2 have no SAMPLES word: their one deterministic frame is "sample 0"
+            sample_count = 1 if self.dialect <= 2 else self.samples
         out = np.zeros((self.height, self.width, 3), np.float32)
         _check(self.lib, self.lib.rtc_render_sum(self.h, seed, sample_begin, sample_count, out))
         return out

@@ -56,6 +56,7 @@ struct DevBuf {
 
 constexpr uint64_t kDefaultBatchPaths = 1ull << 24;
 constexpr int kMaxDepthSlots = 64;
+constexpr int kMaxWhittedDepth = 32;   // course_device.cuh kWhittedStack = kMaxWhittedDepth + 2
 }  // namespace
 
 struct rtc_scene {
@@ -239,7 +240,7 @@ rtc_scene* make_scene(const std::string& text, int device, int dialect = DIALECT
         delete s;
         return nullptr;
     }
-    if (dialect == DIALECT_HW2 && s->host.ray_depth > 32) {
+    if (dialect == DIALECT_HW2 && s->host.ray_depth > (unsigned)kMaxWhittedDepth) {
         fail(RTC_ERR_UNSUPPORTED, "hw2 dialect: RAY_DEPTH above 32 is not supported");
         delete s;
         return nullptr;
@@ -302,6 +303,17 @@ struct Staged {
     }
 };
 #define NEED(ptr) if (!(ptr)) return fail(RTC_ERR_CUDA, "device staging allocation/copy failed")
+
+// the lane streams are non-blocking and joined only into the stream a render was given: whoever reads the
+// counters through another stream waits for the lanes themselves
+cudaError_t sync_lanes(rtc_scene* s) {
+    for (auto& l : s->lanes)
+        if (l.stream) {
+            cudaError_t e = cudaStreamSynchronize(l.stream);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
+}
 
 int ensure_wavefront(rtc_scene* s, uint64_t cap, int nlanes) {
     if (!s->fork) CU(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
@@ -375,6 +387,9 @@ int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]) {
 int rtc_scene_override(rtc_scene* s, int width, int height, int samples, int ray_depth) {
     if (!s) return fail(RTC_ERR_ARG, "null scene");
     if (ray_depth >= 0 && ray_depth + 2 > kMaxDepthSlots) return fail(RTC_ERR_UNSUPPORTED, "RAY_DEPTH above 62 is not supported");
+    // the Whitted kernel keeps its recursion in a per-thread stack of kWhittedStack entries (course_device.cuh)
+    if (ray_depth > kMaxWhittedDepth && s->host.dialect == DIALECT_HW2)
+        return fail(RTC_ERR_UNSUPPORTED, "hw2 dialect: RAY_DEPTH above 32 is not supported");
     if (width >= 0) s->host.cam.width = (unsigned)width;
     if (height >= 0) s->host.cam.height = (unsigned)height;
     if (samples >= 0) s->host.samples = (unsigned)samples;
@@ -548,12 +563,14 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
                           void* stream) {
     int rc = need_device(s);
     if (rc) return rc;
-    if (!accum_dev) return fail(RTC_ERR_ARG, "null accumulation buffer");
     const uint64_t npix = (uint64_t)s->host.cam.width * s->host.cam.height;
     const uint64_t total = npix * sample_count;
-    if (total == 0) return RTC_OK;
+    if (total == 0) return RTC_OK;   // an empty frame (no DIMENSIONS) or an empty sample range: nothing to add
+    if (!accum_dev) return fail(RTC_ERR_ARG, "null accumulation buffer");
     if (s->host.dialect <= DIALECT_HW2) {
-        // hw1 / hw2: one deterministic frame, whatever the sample range (the colour is added once)
+        // hw1 / hw2: ONE deterministic frame = sample 0.  A range that holds sample 0 adds the colour once, any
+        // other range adds nothing, so that sample ranges split over several devices still sum to one frame.
+        if (sample_begin > 0) return RTC_OK;
         LaunchCtx c{(cudaStream_t)stream, s->sms};
         if (s->host.dialect == DIALECT_HW1) launch_raycast_hw1(c, s->dev(), accum_dev);
         else launch_whitted_hw2(c, s->dev(), accum_dev);
@@ -623,6 +640,7 @@ int rtc_render_counters(rtc_scene* s, void* stream, uint64_t out[8]) {
     if (rc) return rc;
     if (!out) return fail(RTC_ERR_ARG, "null argument");
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(sync_lanes(s));
     unsigned long long h[8];
     CU(cudaMemcpy(h, s->stats.p, sizeof h, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) out[i] = h[i];
@@ -653,6 +671,7 @@ int rtc_render_sum(rtc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t 
     if (rc) return rc;
     if (!sum_host) return fail(RTC_ERR_ARG, "null argument");
     size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (nvalues == 0) return RTC_OK;
     CU(s->accum.ensure(nvalues));
     CU(cudaMemset(s->accum.p, 0, nvalues * sizeof(float)));
     if ((rc = rtc_render_accumulate(s, seed, sample_begin, sample_count, s->accum.p, nullptr))) return rc;
@@ -666,6 +685,7 @@ int rtc_render_u8(rtc_scene* s, uint32_t seed, uint8_t* rgb_host) {
     const uint32_t samples = s->host.dialect <= DIALECT_HW2 ? 1u : s->host.samples;  // hw1 / hw2 have no SAMPLES
     if (samples == 0) return fail(RTC_ERR_ARG, "scene has SAMPLES 0");
     size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (nvalues == 0) return RTC_OK;   // no DIMENSIONS: the reference writes a PPM header and no pixels
     CU(s->accum.ensure(nvalues));
     CU(s->rgb.ensure(nvalues));
     CU(cudaMemsetAsync(s->accum.p, 0, nvalues * sizeof(float), nullptr));
@@ -699,6 +719,7 @@ int rtc_render_profile(rtc_scene* s, void* stream, double ms[4], uint64_t launch
     if (rc) return rc;
     if (!ms || !launches) return fail(RTC_ERR_ARG, "null argument");
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(sync_lanes(s));
     s->collect_spans();
     for (int i = 0; i < 4; ++i) { ms[i] = s->prof_ms[i]; launches[i] = s->prof_launches[i]; }
     if (reset) for (int i = 0; i < 4; ++i) { s->prof_ms[i] = 0; s->prof_launches[i] = 0; }

@@ -69,6 +69,7 @@ RT_D vec3 whitted_pixel_hw2(const DevScene& S, uint32_t pixel) {
     while (sp > 0) {
         Pending r = st[--sp];
         if (r.depth == 0) continue;  // hw2 src/scene.cpp:263-265
+        if (sp + 2 > kWhittedStack) continue;  // unreachable while RAY_DEPTH <= 32 (enforced at load and override): never write past st[]
         SceneHit h = closest_hit(S, r.o, r.d);
         if (h.id < 0) { L = L + r.w * mk3(S.bg.x, S.bg.y, S.bg.z); continue; }
         vec3 p = r.o + h.t * r.d;

@@ -31,9 +31,14 @@ int main(int argc, const char* argv[]) {
         std::fprintf(stderr, "raytracing_hw5: %s\n", rtc_last_error());
         return 1;
     }
-    rtc_scene_override(scene, env_int("RTC_WIDTH", -1), env_int("RTC_HEIGHT", -1), env_int("RTC_SAMPLES", -1),
-                       env_int("RTC_RAY_DEPTH", -1));
-    int rc = rtc_render_ppm(scene, (uint32_t)env_int("RTC_SEED", 0), argv[2]);
+    int rc = rtc_scene_override(scene, env_int("RTC_WIDTH", -1), env_int("RTC_HEIGHT", -1), env_int("RTC_SAMPLES", -1),
+                                env_int("RTC_RAY_DEPTH", -1));
+    if (rc != RTC_OK) {
+        std::fprintf(stderr, "raytracing_hw5: %s\n", rtc_last_error());
+        rtc_scene_free(scene);
+        return 1;
+    }
+    rc = rtc_render_ppm(scene, (uint32_t)env_int("RTC_SEED", 0), argv[2]);
     if (rc != RTC_OK) std::fprintf(stderr, "raytracing_hw5: %s\n", rtc_last_error());
     rtc_scene_free(scene);
     return rc == RTC_OK ? 0 : 1;

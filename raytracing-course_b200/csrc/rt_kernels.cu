@@ -443,10 +443,11 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
 __global__ void k_tally(const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     unsigned long long rays = 0, queued = 0;
     for (uint32_t b = 0; b < ray_depth; ++b) { rays += q[b]; queued += tqc[b]; }
-    stats[0] += q[0];
-    stats[1] += rays;
-    stats[3] += 1;
-    stats[7] += queued;
+    // one k_tally per batch on each lane's own stream: two of them may run at the same time
+    atomicAdd(stats + 0, (unsigned long long)q[0]);
+    atomicAdd(stats + 1, rays);
+    atomicAdd(stats + 3, 1ull);
+    atomicAdd(stats + 7, queued);
 }
 
 // Scene::Render's per-pixel tail (src/scene.cpp:201, 227-228, 247): mean, AcesTonemap,

@@ -17,6 +17,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_devices():
+    try:
+        import raytracing_course_b200 as m
+        m.load_library()
+        return m.device_count()
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a CUDA device skips the gpu-marked tests instead of failing them
+    (the product has no CPU path to fall back to)."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: the product has no CPU path")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def scene_path(name):
     """Path of scenes/<name>.txt, generating the scene files on first use."""
     p = os.path.join(SCENES, name + ".txt")

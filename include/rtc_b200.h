@@ -116,6 +116,9 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
  * the scene was created or rtc_render_reset_counters. */
 int rtc_render_counters(rtc_scene* s, void* stream, uint64_t out[8]);
 int rtc_render_reset_counters(rtc_scene* s);
+/* Warp-execution efficiency of k_traverse's per-warp scheduler (only with count_visits): out[0..3] = warp
+ * iterations of kind VISIT / LEAF / FINISH / REFILL, out[4..7] = lanes that took part in them (of 32 each). */
+int rtc_traverse_lanes(rtc_scene* s, void* stream, uint64_t out[8]);
 /* mean = 1/total_samples * sum ; tonemap ; gamma ; u8 -> rgb_dev (3 bytes per pixel, device) */
 int rtc_render_resolve(rtc_scene* s, const float* accum_dev, uint32_t total_samples, uint8_t* rgb_dev, void* stream);
 /* whole Scene::Render with the scene's own SAMPLES: host u8 image (3*W*H bytes) */

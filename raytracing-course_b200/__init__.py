@@ -57,6 +57,7 @@ _SIGNATURES = {
     "rtc_render_accumulate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rtc_render_counters": (C.c_int, [C.c_void_p, C.c_void_p, _u64]),
     "rtc_render_reset_counters": (C.c_int, [C.c_void_p]),
+    "rtc_traverse_lanes": (C.c_int, [C.c_void_p, C.c_void_p, _u64]),
     "rtc_render_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rtc_render_u8": (C.c_int, [C.c_void_p, C.c_uint32, _u8]),
     "rtc_render_sum": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _f32]),
@@ -301,6 +302,15 @@ class Scene:
         _check(self.lib, self.lib.rtc_render_counters(self.h, C.c_void_p(stream or 0), out))
         keys = ["paths", "rays", "launches", "batches", "index_node_visits", "fallback_rays", "prim_tests", "traversed_rays"]
         return dict(zip(keys, [int(v) for v in out[:8]]))
+
+    def traverse_lanes(self, stream=None):
+        """Warp-execution efficiency of k_traverse's scheduler (needs set_profiling(count_visits=True)): per kind
+        (visit, leaf, finish, refill) the warp iterations and the mean number of lanes (of 32) that took part."""
+        out = np.zeros(8, np.uint64)
+        _check(self.lib, self.lib.rtc_traverse_lanes(self.h, C.c_void_p(stream or 0), out))
+        kinds = ["visit", "leaf", "finish", "refill"]
+        return {k: {"iterations": int(out[i]), "lanes": (float(out[4 + i]) / float(out[i]) if out[i] else 0.0)}
+                for i, k in enumerate(kinds)}
 
     def set_profiling(self, kernel_events=False, count_visits=False):
         _check(self.lib, self.lib.rtc_set_profiling(self.h, int(kernel_events), int(count_visits)))

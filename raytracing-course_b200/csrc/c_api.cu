@@ -56,6 +56,7 @@ struct DevBuf {
 
 constexpr uint64_t kDefaultBatchPaths = 1ull << 24;
 constexpr int kMaxDepthSlots = 64;
+constexpr int kStatWords = 16;
 constexpr int kMaxWhittedDepth = 32;   // course_device.cuh kWhittedStack = kMaxWhittedDepth + 2
 }  // namespace
 
@@ -77,27 +78,32 @@ struct rtc_scene {
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf<float4> path[2][4];
-        DevBuf<float> hit_cd[2];             // ping-pong like the path queues
+        bool l2_window_set = false;
+        DevBuf<float4> path[2][3];           // two ping-pong sets of (origin | sample, direction | closest plane, throughput | pixel)
         DevBuf<uint32_t> hit_id[2];
         DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
+        DevBuf<unsigned char> recpool;       // k_traverse_pool: leaf-hit records of the rays resident in its warps
         DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
         void release() {
             for (auto& set : path) for (auto& b : set) b.release();
-            for (auto& b : hit_cd) b.release();
             for (auto& b : hit_id) b.release();
-            trav_queue.release(); queue.release();
+            trav_queue.release(); queue.release(); recpool.release();
             if (done) cudaEventDestroy(done);
             if (stream) cudaStreamDestroy(stream);
             done = nullptr; stream = nullptr;
+            l2_window_set = false;
         }
     };
     static constexpr int kMaxLanes = 4;
     Lane lanes[kMaxLanes];
     int nlanes = 2;                      // env RTC_STREAMS (1..4)
+    bool l2_persist = false;             // env RTC_L2_PERSIST: pin the scene arena in L2 (access-policy window per lane)
+    size_t l2_window_bytes = 0;
+    size_t prop_persist_max = 0, prop_window_max = 0;
     cudaEvent_t fork = nullptr;
-    DevBuf<unsigned long long> stats;    // 8 words
+    DevBuf<unsigned long long> stats;    // 16 words: rtc_render_counters (8) + rtc_traverse_lanes (8)
     DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
+    DevBuf<float4> accum4;               // per-pixel float4 sums of the frame being rendered (k_shade deposits, k_fold reads)
     DevBuf<uint8_t> rgb;
     uint64_t launches = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -156,7 +162,7 @@ struct rtc_scene {
         for (auto& l : lanes) l.release();
         if (fork) cudaEventDestroy(fork);
         fork = nullptr;
-        stats.release(); accum.release(); rgb.release();
+        stats.release(); accum.release(); accum4.release(); rgb.release();
         collect_spans();
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
         event_pool.clear();
@@ -211,9 +217,19 @@ int upload_scene(rtc_scene* s, uint64_t* h2d) {
     CU(cudaMemcpyAsync(s->arena_dev, s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, nullptr));
     CU(cudaStreamSynchronize(nullptr));
     const uint64_t bytes = payload;
+    if (const char* v = std::getenv("RTC_L2_PERSIST")) {
+        if (std::atoi(v) > 0 && s->prop_persist_max > 0 && !s->l2_persist) {
+            size_t want = s->arena_bytes + (s->arena_bytes >> 2);
+            if (want > s->prop_persist_max) want = s->prop_persist_max;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                s->l2_persist = true;
+                s->l2_window_bytes = s->arena_bytes < s->prop_window_max ? s->arena_bytes : s->prop_window_max;
+            } else cudaGetLastError();
+        }
+    }
     if (!s->stats.p) {
-        CU(s->stats.ensure(8));
-        CU(cudaMemset(s->stats.p, 0, 8 * sizeof(unsigned long long)));
+        CU(s->stats.ensure(kStatWords));
+        CU(cudaMemset(s->stats.p, 0, kStatWords * sizeof(unsigned long long)));
     }
     s->device_bytes = bytes;
     if (h2d) *h2d = bytes;
@@ -265,6 +281,8 @@ rtc_scene* make_scene(const std::string& text, int device, int dialect = DIALECT
         cudaDeviceProp prop;
         cudaGetDeviceProperties(&prop, device);
         s->sms = prop.multiProcessorCount;
+        s->prop_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+        s->prop_window_max = (size_t)prop.accessPolicyMaxWindowSize;
         if (upload_scene(s, nullptr) != RTC_OK) {
             s->release_device();
             delete s;
@@ -321,10 +339,23 @@ int ensure_wavefront(rtc_scene* s, uint64_t cap, int nlanes) {
         rtc_scene::Lane& l = s->lanes[i];
         if (!l.stream) CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         if (!l.done) CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        if (s->l2_persist && !l.l2_window_set) {
+            // the scene arena (BVH nodes, triangles: what k_traverse gathers from) stays in L2 while the wavefront
+            // state streams through it
+            cudaStreamAttrValue attr;
+            std::memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = s->arena_dev;
+            attr.accessPolicyWindow.num_bytes = s->l2_window_bytes;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CU(cudaStreamSetAttribute(l.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+            l.l2_window_set = true;
+        }
         for (auto& set : l.path) for (auto& b : set) CU(b.ensure(cap));
-        for (auto& b : l.hit_cd) CU(b.ensure(cap));
         for (auto& b : l.hit_id) CU(b.ensure(cap));
         CU(l.trav_queue.ensure(cap));
+        CU(l.recpool.ensure(traverse_pool_record_bytes(s->sms)));
         CU(l.queue.ensure(3 * kMaxDepthSlots));
     }
     return RTC_OK;
@@ -440,7 +471,7 @@ int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, in
     if (rc) return rc;
     if (n < 0 || !o || !d || !id || !t || !normal || !interior) return fail(RTC_ERR_ARG, "bad argument");
     if (n == 0) return RTC_OK;
-    if ((uint64_t)n > (1ull << 30)) return fail(RTC_ERR_ARG, "too many rays in one call");
+    if ((uint64_t)n > (1ull << 28)) return fail(RTC_ERR_ARG, "too many rays in one call (limit 2^28)");
     Staged st;
     float* od = st.in(o, 3 * (size_t)n); NEED(od);
     float* dd = st.in(d, 3 * (size_t)n); NEED(dd);
@@ -449,10 +480,10 @@ int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, in
     float* nd = st.out<float>(3 * (size_t)n); NEED(nd);
     int32_t* ind = st.out<int32_t>((size_t)n); NEED(ind);
     // the same kernels as the render path: rays into the float4 queue layout, extend, read back
-    PathSoA P{st.out<float4>((size_t)n), st.out<float4>((size_t)n), nullptr, nullptr};
+    PathSoA P{st.out<float4>((size_t)n), st.out<float4>((size_t)n), nullptr};
     NEED(P.o); NEED(P.d);
-    HitSoA H{st.out<float>((size_t)n), st.out<uint32_t>((size_t)n)};
-    NEED(H.cd); NEED(H.id);
+    HitSoA H{st.out<uint32_t>((size_t)n)};
+    NEED(H.id);
     uint32_t* tq = st.out<uint32_t>((size_t)n); NEED(tq);
     uint32_t* q = st.out<uint32_t>(4); NEED(q);
     CU(cudaMemset(q, 0, 4 * sizeof(uint32_t)));
@@ -462,7 +493,8 @@ int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, in
     if (mode == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, P, H, q, (uint32_t)n);
     else {
         launch_pre(c, S, P, H, q, (uint32_t)n, tq, q + 1);
-        launch_traverse(c, S, P, H, (uint32_t)n, tq, q + 1, q + 2, false, s->stats.p);
+        unsigned char* recpool = st.out<unsigned char>(traverse_pool_record_bytes(s->sms)); NEED(recpool);
+        launch_traverse(c, S, P, H, (uint32_t)n, tq, q + 1, q + 2, false, s->stats.p, recpool);
     }
     launch_unpack_hits(c, S, n, P, H, idd, td, nd, ind);
     CU(cudaGetLastError());
@@ -591,6 +623,8 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     const int nlanes = s->profiling ? 1 : (int)(nbatches < (uint64_t)s->nlanes ? nbatches : (uint64_t)s->nlanes);
     if ((rc = ensure_wavefront(s, cap, nlanes))) return rc;
     cudaStream_t user = (cudaStream_t)stream;
+    CU(s->accum4.ensure(npix));
+    CU(cudaMemsetAsync(s->accum4.p, 0, npix * sizeof(float4), user));
     DevScene S = s->dev();
     // fork: the lane streams start after everything already queued on the caller's stream
     CU(cudaEventRecord(s->fork, user));
@@ -604,9 +638,9 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         uint32_t* cursor = L.queue.p + 2 * kMaxDepthSlots; // k_traverse work cursors, per bounce
         uint32_t count = (uint32_t)((total - first) < cap ? (total - first) : cap);
         CU(cudaMemsetAsync(L.queue.p, 0, 3 * kMaxDepthSlots * sizeof(uint32_t), st));
-        PathSoA cur{L.path[0][0].p, L.path[0][1].p, L.path[0][2].p, L.path[0][3].p};
-        PathSoA nxt{L.path[1][0].p, L.path[1][1].p, L.path[1][2].p, L.path[1][3].p};
-        HitSoA hcur{L.hit_cd[0].p, L.hit_id[0].p}, hnxt{L.hit_cd[1].p, L.hit_id[1].p};
+        PathSoA cur{L.path[0][0].p, L.path[0][1].p, L.path[0][2].p};
+        PathSoA nxt{L.path[1][0].p, L.path[1][1].p, L.path[1][2].p};
+        HitSoA hcur{L.hit_id[0].p}, hnxt{L.hit_id[1].p};
         s->span_begin(0, st);
         launch_generate(c, S, cur, hcur, L.queue.p, L.trav_queue.p, tqc, first, count, seed, sample_begin);
         s->span_end(st);
@@ -614,11 +648,12 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         for (uint32_t b = 1; b <= depth; ++b) {
             s->span_begin(1, st);
             if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, L.queue.p + (b - 1), count);
-            else launch_traverse(c, S, cur, hcur, count, L.trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
+            else launch_traverse(c, S, cur, hcur, count, L.trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p,
+                                 L.recpool.p);
             s->span_end(st);
             s->span_begin(2, st);
             launch_shade(c, S, cur, hcur, nxt, hnxt, L.queue.p + (b - 1), L.queue.p + b, L.trav_queue.p, tqc + b, count,
-                         accum_dev, b, seed);
+                         s->accum4.p, b, seed);
             s->span_end(st);
             s->launches += 2;
             PathSoA tmp = cur; cur = nxt; nxt = tmp;
@@ -632,6 +667,8 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         CU(cudaEventRecord(s->lanes[i].done, s->lanes[i].stream));
         CU(cudaStreamWaitEvent(user, s->lanes[i].done, 0));
     }
+    launch_fold(LaunchCtx{user, s->sms}, s->accum4.p, accum_dev, (uint32_t)npix);
+    s->launches++;
     CU(cudaGetLastError());
     return RTC_OK;
 }
@@ -647,10 +684,21 @@ int rtc_render_counters(rtc_scene* s, void* stream, uint64_t out[8]) {
     out[2] = s->launches;
     return RTC_OK;
 }
+int rtc_traverse_lanes(rtc_scene* s, void* stream, uint64_t out[8]) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!out) return fail(RTC_ERR_ARG, "null argument");
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    CU(sync_lanes(s));
+    unsigned long long h[8];
+    CU(cudaMemcpy(h, s->stats.p + 8, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out[i] = h[i];
+    return RTC_OK;
+}
 int rtc_render_reset_counters(rtc_scene* s) {
     int rc = need_device(s);
     if (rc) return rc;
-    CU(cudaMemset(s->stats.p, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->stats.p, 0, kStatWords * sizeof(unsigned long long)));
     s->launches = 0;
     return RTC_OK;
 }

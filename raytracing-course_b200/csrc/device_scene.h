@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "scene_host.h"
 
@@ -18,7 +19,7 @@ struct DevScene {
     const float4* xf_rot;  // quaternion xyzw
     const float4* mat0;    // (colour, bits(material))
     const float4* mat1;    // (emission, ior)
-    // index BVH: 6 float4 (96 B) per 4-wide node: fp16 child boxes, child refs, fp16 child direction cones
+    // index BVH: 8 float4 (128 B) per 4-wide node, child-major (scene_host.h kIndexNodeF4)
     const float4* inodes;
     // reference BVH: 2 float4 per node + meta
     const float4* rnodes;
@@ -30,6 +31,7 @@ struct DevScene {
     const float4* plights; // hw2 dialect: 4 float4 per light (intensity, bits(directed)) (pos) (attenuation) (unit dir)
 
     uint32_t nprims, nbvh, nnodes, root, iroot, lca_levels, nlights, ref_depth;
+    uint32_t iroot_ref[4];  // child references of the index root (k_traverse starts from the children pre_step entered)
     uint32_t width, height, ray_depth, nplanes;
     float3 cam_pos, cam_right, cam_up, cam_forward;
     float tan_fov_x, tan_fov_y;
@@ -48,6 +50,11 @@ inline void fill_dev_scalars(const HostScene& host, DevScene& S) {
     S.nplanes = (uint32_t)(host.flat.planes.size() / 2);
     S.nprims = (uint32_t)host.prims.size(); S.nbvh = host.nbvh; S.nnodes = (uint32_t)host.nodes.size();
     S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
+    for (int c = 0; c < 4; ++c) S.iroot_ref[c] = IREF_NONE;
+    if (host.flat.iroot != IREF_NONE && !(host.flat.iroot & IREF_LEAF)) {
+        for (int c = 0; c < 4; ++c)   // the last word of each child
+            memcpy(&S.iroot_ref[c], &host.flat.inodes[kIndexNodeF4 * (size_t)host.flat.iroot + kIndexChildF4 * c + 1].w, 4);
+    }
     S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;
     S.width = host.cam.width; S.height = host.cam.height; S.ray_depth = host.ray_depth;
     S.cam_pos = make_float3(host.cam.pos.x, host.cam.pos.y, host.cam.pos.z);
@@ -68,16 +75,15 @@ inline void fill_dev_scalars(const HostScene& host, DevScene& S) {
     S.ambient = make_float3(host.ambient.x, host.ambient.y, host.ambient.z);
 }
 
-// wavefront path state, structure of float4 arrays
+// Wavefront path state: three float4 per path and one word for the hit (52 bytes).  Radiance does not travel with
+// the path: beta * emission is added to the pixel sum where it is found (k_shade).
 struct PathSoA {
-    float4* o;      // origin.xyz, -
-    float4* d;      // direction.xyz, -
+    float4* o;      // origin.xyz, bits(sample index)
+    float4* d;      // direction.xyz, distance of the closest plane (1e18 = none): closest_dist handed to the BVH
     float4* beta;   // throughput.rgb, bits(pixel index)
-    float4* rad;    // radiance so far .rgb, bits(sample index)
 };
 struct HitSoA {
-    float* cd;      // distance of the closest plane (1e18 = none): closest_dist handed to the BVH
-    uint32_t* id;   // 0xFFFFFFFF = miss, else id of the closest primitive
+    uint32_t* id;   // 0xFFFFFFFF = miss, else id of the closest primitive (plane so far, k_traverse overwrites)
 };
 
 constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;

@@ -1,0 +1,234 @@
+// peaks.cu -- the roofs k_traverse / k_shade are measured against, as three micro-kernels (sm_100a):
+//   1. an L2-resident random gather of 96-byte records (the index-BVH node fetch pattern: three 32-byte
+//      sectors of one record at a random position of a table as large as the dragon scene, 36 MB), GB/s;
+//   2. warp-instruction issue rates: independent FFMA chains (FMA pipe), an IADD3 / LOP3 / FMNMX mix (ALU
+//      pipe) and both interleaved (the scheduler's 1 instruction / clock / sub-partition limit);
+//   3. a streaming copy (HBM), for comparison with MEASURED_PEAKS.json.
+// Built by tools/peaks/Makefile into libpeaks.so (rtc_peaks_measure, called live by bench.py on the GPU it
+// benchmarks) and the `peaks` command (prints the same JSON).  Not part of the product library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#ifndef PEAKS_FIRST_PASS
+#include "peaks_counts.h"   // K_FFMA_LOOP_INSTR, K_ALU_LOOP_INSTR, K_MIXED_LOOP_INSTR: from the SASS (Makefile)
+#else
+#define K_FFMA_LOOP_INSTR 1
+#define K_ALU_LOOP_INSTR 1
+#define K_MIXED_LOOP_INSTR 1
+#endif
+
+namespace {
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
+// every thread: `iters` rounds of UNROLL independent 96-byte gathers at hashed record indices
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k_gather96(const float4* table, uint32_t nrec, int iters, float* sink) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    uint32_t h = mix32(tid * 2654435761u + 12345u);
+    for (int i = 0; i < iters; ++i) {
+        float4 a[UNROLL], b[UNROLL], c[UNROLL], d[UNROLL], e[UNROLL], f[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            h = mix32(h + 0x9E3779B9u);
+            const float4* rec = table + 6 * (size_t)(h % nrec);
+            ldg256(rec, a[u], b[u]);
+            ldg256(rec + 2, c[u], d[u]);
+            ldg256(rec + 4, e[u], f[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) acc += a[u].x + b[u].y + c[u].z + d[u].w + e[u].x + f[u].y;
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
+// the same gather, one DEPENDENT chain per thread (next index from the fetched record): latency-bound,
+// what a lane of k_traverse sees when it walks down the tree
+__global__ void __launch_bounds__(128) k_chase96(const float4* table, uint32_t nrec, int iters, float* sink) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t h = mix32(tid * 2654435761u + 777u);
+    float acc = 0.f;
+    for (int i = 0; i < iters; ++i) {
+        const float4* rec = table + 6 * (size_t)(h % nrec);
+        float4 a, b, c, d, e, f;
+        ldg256(rec, a, b); ldg256(rec + 2, c, d); ldg256(rec + 4, e, f);
+        acc += b.y + d.w + f.y;
+        h = mix32(h + __float_as_uint(a.x) + __float_as_uint(c.z) + __float_as_uint(e.x));
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_ffma(int iters, float* sink, long long* clocks) {
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-7f;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    long long t1 = clock64();
+    float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456f) sink[0] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) clocks[0] = t1 - t0;
+}
+// ALU pipe: integer add, 3-input logic and float min/max chains (the instructions k_traverse's bookkeeping is made of)
+__global__ void __launch_bounds__(256) k_alu(int iters, float* sink) {
+    uint32_t a0 = threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
+    float f0 = threadIdx.x, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3;
+    const uint32_t k = blockIdx.x | 0x55u;
+    const float lo = (float)blockIdx.x, hi = lo + 1e6f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = (a0 ^ k) + a1; a1 = (a1 & a2) | (a3 ^ k); a2 = a2 + a3 + k; a3 = (a3 | a0) ^ a1;
+            f0 = fminf(fmaxf(f0, lo), f1); f1 = fmaxf(fminf(f1, hi), f2); f2 = fminf(f2, f3); f3 = fmaxf(f3, f0);
+        }
+    }
+    uint32_t s = a0 + a1 + a2 + a3;
+    float fs = f0 + f1 + f2 + f3;
+    if (s == 0x12345678u && fs == 1.5f) sink[0] = fs;
+}
+// both pipes interleaved: the issue limit (1 warp instruction per clock and sub-partition)
+__global__ void __launch_bounds__(256) k_mixed(int iters, float* sink) {
+    uint32_t a0 = threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
+    float f0 = threadIdx.x, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3;
+    const uint32_t k = blockIdx.x | 0x55u;
+    const float m = 1.0000001f, c = 1e-7f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = (a0 ^ k) + a1; f0 = fmaf(f0, m, c); a1 = (a1 & a2) | (a3 ^ k); f1 = fmaf(f1, m, c);
+            a2 = a2 + a3 + k; f2 = fmaf(f2, m, c); a3 = (a3 | a0) ^ a1; f3 = fmaf(f3, m, c);
+        }
+    }
+    uint32_t s = a0 + a1 + a2 + a3;
+    float fs = f0 + f1 + f2 + f3;
+    if (s == 0x12345678u && fs == 1.5f) sink[0] = fs;
+}
+__global__ void __launch_bounds__(256) k_copy(const float4* __restrict__ src, float4* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_fill(float4* p, size_t n, uint32_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = mix32((uint32_t)i + seed);
+        p[i] = make_float4(__uint_as_float(h & 0x3FFFFFFFu), 1.f, __uint_as_float(mix32(h) & 0x3FFFFFFFu), 2.f);
+    }
+}
+
+template <class F>
+double best_ms(F launch, int reps) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 1e30;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(a);
+        launch();
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms < best) best = ms;   // the first repetition warms caches and clocks
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return best;
+}
+
+}  // namespace
+
+// out[0] L2 gather GB/s (96-byte records, table_mb MB table, independent gathers)
+// out[1] the same with one dependent chain per thread (GB/s) and out[2] its latency per fetch in ns
+// out[3] FFMA warp-instructions / s (G), out[4] ALU-mix warp-instructions / s (G), out[5] interleaved (G)
+// out[6] SM clock seen by the FFMA kernel (MHz), out[7] streaming copy GB/s (read + write), out[8] SM count
+// out[9] FP32 TFLOP/s of the FFMA kernel
+extern "C" int rtc_peaks_measure(int device, double table_mb, double out[10]) {
+    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 1;
+    const int sms = prop.multiProcessorCount;
+    std::memset(out, 0, 10 * sizeof(double));
+    out[8] = sms;
+    float* sink = nullptr;
+    long long* clocks = nullptr;
+    cudaMalloc(&sink, 64);
+    cudaMalloc(&clocks, 64);
+    // ---- 1. gather
+    const uint32_t nrec = (uint32_t)(table_mb * 1e6 / 96.0);
+    float4* table = nullptr;
+    if (cudaMalloc(&table, (size_t)nrec * 96) != cudaSuccess) return 2;
+    k_fill<<<sms * 8, 256>>>(table, (size_t)nrec * 6, 1u);
+    {
+        const int grid = sms * 8, iters = 16;
+        const double ms = best_ms([&] { k_gather96<4><<<grid, 256>>>(table, nrec, iters, sink); }, 6);
+        out[0] = (double)grid * 256 * iters * 4 * 96.0 / (ms * 1e-3) / 1e9;
+    }
+    {
+        const int grid = sms * 7, iters = 64;   // k_traverse's residency: 7 blocks of 128 threads per SM
+        const double ms = best_ms([&] { k_chase96<<<grid, 128>>>(table, nrec, iters, sink); }, 6);
+        out[1] = (double)grid * 128 * iters * 96.0 / (ms * 1e-3) / 1e9;
+        out[2] = ms * 1e6 / iters;
+    }
+    cudaFree(table);
+    // ---- 2. issue rates
+    {
+        const int grid = sms * 8, iters = 2048;
+        double ms = best_ms([&] { k_ffma<<<grid, 256>>>(iters, sink, clocks); }, 5);
+        const double winst = (double)grid * 8 * iters * K_FFMA_LOOP_INSTR;   // warps x instructions (64 FFMA + loop control)
+        out[3] = winst / (ms * 1e-3) / 1e9;
+        out[9] = (double)grid * 8 * iters * 64 * 32 * 2 / (ms * 1e-3) / 1e12;
+        long long cyc = 0;
+        cudaMemcpy(&cyc, clocks, sizeof cyc, cudaMemcpyDeviceToHost);
+        // clock64 over the loop of block 0 against the kernel's duration: a lower bound of the SM clock
+        out[6] = (double)cyc / (ms * 1e-3) / 1e6;
+        ms = best_ms([&] { k_alu<<<grid, 256>>>(iters, sink); }, 5);
+        out[4] = (double)grid * 8 * iters * K_ALU_LOOP_INSTR / (ms * 1e-3) / 1e9;
+        ms = best_ms([&] { k_mixed<<<grid, 256>>>(iters, sink); }, 5);
+        out[5] = (double)grid * 8 * iters * K_MIXED_LOOP_INSTR / (ms * 1e-3) / 1e9;
+    }
+    // ---- 3. copy
+    {
+        const size_t n = (size_t)1 << 26;  // 1 GiB each way
+        float4 *a = nullptr, *b = nullptr;
+        if (cudaMalloc(&a, n * 16) == cudaSuccess && cudaMalloc(&b, n * 16) == cudaSuccess) {
+            k_fill<<<sms * 8, 256>>>(a, n, 3u);
+            const double ms = best_ms([&] { k_copy<<<sms * 16, 256>>>(a, b, n); }, 5);
+            out[7] = 2.0 * n * 16 / (ms * 1e-3) / 1e9;
+        }
+        cudaFree(a); cudaFree(b);
+    }
+    cudaFree(sink); cudaFree(clocks);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : 3;
+}
+
+#ifdef PEAKS_MAIN
+int main(int argc, char** argv) {
+    double out[10];
+    const double mb = argc > 1 ? atof(argv[1]) : 36.0;
+    int rc = rtc_peaks_measure(0, mb, out);
+    if (rc) { std::fprintf(stderr, "peaks: failed (%d)\n", rc); return 1; }
+    std::printf("{\"table_mb\": %.1f, \"l2_gather96_gbs\": %.1f, \"l2_chase96_gbs\": %.1f, \"l2_chase96_ns_per_fetch\": %.1f, "
+                "\"ffma_gwinst_s\": %.1f, \"alu_gwinst_s\": %.1f, \"mixed_gwinst_s\": %.1f, \"sm_mhz_seen\": %.0f, "
+                "\"copy_gbs\": %.1f, \"sms\": %d, \"fp32_tflops\": %.2f}\n",
+                mb, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7], (int)out[8], out[9]);
+    return 0;
+}
+#endif

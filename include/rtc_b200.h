@@ -85,6 +85,10 @@ void rtc_set_traversal(rtc_scene* s, int mode);
  *      o,d: 3 floats per ray.  id = -1 on a miss (t, normal, interior then 0). */
 int rtc_intersect(const rtc_scene* s, long n, const float* o_host, const float* d_host,
                   int32_t* id_host, float* t_host, float* normal_host, int32_t* interior_host, int mode);
+/* the same with every array already on the scene's device (3 floats per origin / direction / normal), asynchronous
+ * on `stream`, on scratch buffers the scene keeps: the form to use at rate (tens of millions of rays per call) */
+int rtc_intersect_dev(rtc_scene* s, long n, const float* o_dev, const float* d_dev, int32_t* id_dev, float* t_dev,
+                      float* normal_dev, int32_t* interior_dev, int mode, void* stream);
 /* ---- Primitive::Intersect (src/primitives.cpp:14-52) of one primitive (final-order id) */
 int rtc_primitive_intersect(const rtc_scene* s, int prim, long n, const float* o_host, const float* d_host,
                             int32_t* hit_host, float* t_host, float* normal_host, int32_t* interior_host);
@@ -127,6 +131,25 @@ int rtc_render_u8(rtc_scene* s, uint32_t seed, uint8_t* rgb_host);
 int rtc_render_sum(rtc_scene* s, uint32_t seed, uint32_t sample_begin, uint32_t sample_count, float* sum_host);
 /* run.sh <scene> <out.ppm> in one call: "P6\nW H\n255\n" + bytes (src/scene.cpp:206-208,243-251) */
 int rtc_render_ppm(rtc_scene* s, uint32_t seed, const char* out_path);
+/* ---- Scene::Render on several devices of this process (src/scene.cpp:205-252 uses every hardware thread of the
+ *      machine, :212): the samples are split over devices[0..ndev) (a device may be listed more than once), each
+ *      renders its range into its own buffer, and devices[0] sums them where they lie -- peer access over NVLink --
+ *      and resolves to 8 bits in the same kernel.  sum_host (optional, 3 floats per pixel) receives the float sums.
+ *      run.sh takes the list from RTC_DEVICES ("0,1,2,3" or "0-7"). */
+int rtc_render_u8_multi(rtc_scene* s, const int* devices, int ndev, uint32_t seed, uint8_t* rgb_host, float* sum_host);
+int rtc_render_ppm_multi(rtc_scene* s, const int* devices, int ndev, uint32_t seed, const char* out_path);
+/* ---- frames in flight: what run.sh does with a parsed scene (flattened scene host -> HBM, render, resolve, 8-bit
+ *      image HBM -> host), queued without host synchronisation.  rtc_frame_begin uploads into the arena that is not
+ *      being read (rtc_scene_upload_async: on a copy stream, under the kernels of the frame before), renders with the
+ *      scene's own SAMPLES on the slot's stream and starts the image on its way to a pinned buffer; rtc_frame_end
+ *      waits for the slot and copies the image out.  slot = 0 or 1: two frames may be in flight. */
+int rtc_scene_upload_async(rtc_scene* s, uint64_t* h2d_bytes);
+int rtc_frame_begin(rtc_scene* s, uint32_t seed, int slot, uint64_t* h2d_bytes);
+int rtc_frame_end(rtc_scene* s, int slot, uint8_t* rgb_host);
+/* resolve a device accumulation buffer (after a reduce over ranks) and start its 8-bit image towards the host on a
+ * stream of its own; rtc_host_image_wait waits for the last one and copies it out (rgb_host may be NULL) */
+int rtc_resolve_to_host_async(rtc_scene* s, const float* accum_dev, uint32_t total_samples, void* stream);
+int rtc_host_image_wait(rtc_scene* s, uint8_t* rgb_host);
 /* Instrumentation (off by default).  kernel_events: bracket every wavefront kernel with CUDA
  * events on the launching stream; count_visits: use the extend-kernel variant that counts
  * index-BVH node visits and primitive tests (counters 4 and 6 of rtc_render_counters).

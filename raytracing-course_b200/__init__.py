@@ -58,6 +58,15 @@ _SIGNATURES = {
     "rtc_render_counters": (C.c_int, [C.c_void_p, C.c_void_p, _u64]),
     "rtc_render_reset_counters": (C.c_int, [C.c_void_p]),
     "rtc_traverse_lanes": (C.c_int, [C.c_void_p, C.c_void_p, _u64]),
+    "rtc_intersect_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_void_p]),
+    "rtc_render_u8_multi": (C.c_int, [C.c_void_p, _i32, C.c_int, C.c_uint32, _u8, C.c_void_p]),
+    "rtc_render_ppm_multi": (C.c_int, [C.c_void_p, _i32, C.c_int, C.c_uint32, C.c_char_p]),
+    "rtc_scene_upload_async": (C.c_int, [C.c_void_p, _u64]),
+    "rtc_frame_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _u64]),
+    "rtc_frame_end": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "rtc_resolve_to_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "rtc_host_image_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rtc_render_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rtc_render_u8": (C.c_int, [C.c_void_p, C.c_uint32, _u8]),
     "rtc_render_sum": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _f32]),
@@ -284,6 +293,46 @@ class Scene:
         out = np.zeros((self.height, self.width, 3), np.uint8)
         _check(self.lib, self.lib.rtc_render_u8(self.h, seed, out))
         return out
+
+    def RenderMulti(self, devices, seed=0, want_sum=False):
+        """Scene::Render on several CUDA devices of this process: samples split over `devices`, summed over peer
+        access and resolved on devices[0].  Returns the 8-bit image (and the float sums with want_sum)."""
+        dv = np.asarray(devices, np.int32)
+        out = np.zeros((self.height, self.width, 3), np.uint8)
+        total = np.zeros((self.height, self.width, 3), np.float32) if want_sum else None
+        _check(self.lib, self.lib.rtc_render_u8_multi(self.h, dv, len(dv), seed, out,
+                                                      total.ctypes.data_as(C.c_void_p) if want_sum else None))
+        return (out, total) if want_sum else out
+
+    def upload_async(self):
+        """Queue the H2D copy of the flattened scene into the arena that is not being read; the next render waits for it."""
+        n = np.zeros(1, np.uint64)
+        _check(self.lib, self.lib.rtc_scene_upload_async(self.h, n))
+        return int(n[0])
+
+    def frame_begin(self, seed=0, slot=0):
+        """Queue one whole frame (scene upload, render, resolve, image to a pinned host buffer); returns the H2D bytes."""
+        n = np.zeros(1, np.uint64)
+        _check(self.lib, self.lib.rtc_frame_begin(self.h, seed, slot, n))
+        return int(n[0])
+
+    def frame_end(self, slot=0, out=None):
+        """Wait for the frame of `slot`; copies the image into `out` (uint8, H x W x 3) when given."""
+        _check(self.lib, self.lib.rtc_frame_end(self.h, slot, out.ctypes.data_as(C.c_void_p) if out is not None else None))
+        return out
+
+    def resolve_to_host(self, accum_ptr, total_samples, stream=None):
+        _check(self.lib, self.lib.rtc_resolve_to_host_async(self.h, C.c_void_p(accum_ptr), total_samples, C.c_void_p(stream or 0)))
+
+    def host_image_wait(self, out=None):
+        _check(self.lib, self.lib.rtc_host_image_wait(self.h, out.ctypes.data_as(C.c_void_p) if out is not None else None))
+        return out
+
+    def intersect_dev(self, n, o_ptr, d_ptr, id_ptr, t_ptr, normal_ptr, interior_ptr, mode=0, stream=None):
+        """Scene::RayIntersection on device arrays (pointers as integers), asynchronous on `stream`."""
+        _check(self.lib, self.lib.rtc_intersect_dev(self.h, n, C.c_void_p(o_ptr), C.c_void_p(d_ptr), C.c_void_p(id_ptr),
+                                                    C.c_void_p(t_ptr), C.c_void_p(normal_ptr), C.c_void_p(interior_ptr),
+                                                    mode, C.c_void_p(stream or 0)))
 
     def RenderPPM(self, path, seed=0):
         _check(self.lib, self.lib.rtc_render_ppm(self.h, seed, os.fsencode(path)))

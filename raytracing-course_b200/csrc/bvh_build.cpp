@@ -242,7 +242,7 @@ static uint16_t half_up(float f) {
 
 struct IndexBuilder {
     const std::vector<Unit>& units;
-    std::vector<f4>& out;  // kIndexNodeF4 f4 (128 bytes) per 4-wide node
+    std::vector<f4>& out;  // kIndexNodeF4 f4 (96 bytes) per 4-wide node
     std::vector<float> rarea;
     uint32_t max_depth = 0;
     double slack = 0;  // absolute inflation of every child half-extent: 2^-20 of the scene size (set by HostScene::init)
@@ -423,47 +423,69 @@ struct IndexBuilder {
         }
         uint32_t me = (uint32_t)(out.size() / kIndexNodeF4);
         out.resize(out.size() + kIndexNodeF4, f4{0, 0, 0, 0});
-        for (int i = 0; i < W; ++i) {
-            const bool used = i < (int)slots.size();
-            // unused slot: a far-away point box and the IREF_NONE marker
-            const Aabb bx = used ? slots[i].box : Aabb{{60000.f, 60000.f, 60000.f}, {60000.f, 60000.f, 60000.f}};
-            const float mn[3] = {bx.mn.x, bx.mn.y, bx.mn.z}, mx[3] = {bx.mx.x, bx.mx.y, bx.mx.z};
-            float centre[3];
-            uint16_t half[3];
-            for (int a = 0; a < 3; ++a) {
-                // centre in fp32, half-extent as the smallest fp16 that covers the box from that centre, + slack: the
-                // device evaluates fma(c, 1/d, -(o * 1/d)) -+ h |1/d|, whose rounding is a few ulp of |o / d| and
-                // |c / d|, i.e. a few 2^-24 of the scene size in world units
-                float c = 0.5f * (mn[a] + mx[a]);
-                if (!std::isfinite(c)) c = 0.f;
-                const double need = std::max((double)mx[a] - (double)c, (double)c - (double)mn[a]) + slack;
-                float nf = (float)need;
-                if ((double)nf < need) nf = std::nextafter(nf, INFINITY);
-                centre[a] = c;
-                half[a] = (need <= 65504.0) ? half_up(nf) : (uint16_t)0x7C00u;   // beyond fp16: always visited
-            }
-            uint16_t axis[3] = {0, 0, 0}, thr16 = 0;   // threshold 0 = never culled
-            if (used && !slots[i].cone.open()) {
-                // The device culls the child when |dn . axis| < threshold, dn = normalised ray direction, all in
-                // half precision: the axis components round to nearest (error <= 8.7e-4 in the dot product), dn
-                // likewise, four half products / sums add <= 2.5e-3; the threshold gives 8e-3 away and is
-                // rounded down.  A threshold that ends up <= 0 leaves the child unrestricted.
-                const Cone& c = slots[i].cone;
-                const double thr = std::cos(std::min(c.alpha + 2e-3, 1.5707963)) - 8e-3;
-                if (thr > 0) {
-                    axis[0] = half_bits_rn((float)c.ax); axis[1] = half_bits_rn((float)c.ay); axis[2] = half_bits_rn((float)c.az);
-                    thr16 = half_down((float)thr);
-                    if (thr16 & 0x8000u) thr16 = 0;
+        // one block of 4 children after the other (a node of width 8 is two blocks of the same layout)
+        for (int blk = 0; blk < W / 4; ++blk) {
+            uint16_t hv[6][4];
+            uint16_t cv[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // axis x, y, z, threshold; all 0 = never culled
+            uint32_t refs[4];
+            for (int i = 0; i < 4; ++i) {
+                const int si = 4 * blk + i;  // slot of the node = child i of block blk
+                bool used = si < (int)slots.size();
+                // unused slot: a far-away point box and the IREF_NONE marker
+                Aabb bx = used ? slots[si].box : Aabb{{60000.f, 60000.f, 60000.f}, {60000.f, 60000.f, 60000.f}};
+#if RTC_NODE_CENTRE_HALF
+                // centre rounded to the nearest half, half-extent rounded UP so that [c - h, c + h] covers the box
+                const float mn[3] = {bx.mn.x, bx.mn.y, bx.mn.z}, mx[3] = {bx.mx.x, bx.mx.y, bx.mx.z};
+                for (int a = 0; a < 3; ++a) {
+                    uint16_t c16 = half_bits_rn(0.5f * (mn[a] + mx[a]));
+                    double c = (double)half_to_float(c16);
+                    // + slack: the device evaluates fma(c, 1/d, -(o * 1/d)) -+ h |1/d|, whose rounding is a few ulp of
+                    // |o / d| and |c / d|, i.e. a few 2^-24 of the scene size in world units; the child boxes must stay
+                    // conservative even when a face is exactly representable in fp16 (no rounding margin of its own)
+                    double need = std::max((double)mx[a] - c, c - (double)mn[a]) + slack;
+                    float nf = (float)need;
+                    if ((double)nf < need) nf = std::nextafter(nf, INFINITY);
+                    hv[a][i] = c16;
+                    hv[3 + a][i] = half_up(nf);
+                    if ((c16 & 0x7C00u) == 0x7C00u || !(need <= 65504.0)) { hv[a][i] = 0; hv[3 + a][i] = 0x7C00u; }  // beyond fp16: always visited
                 }
+#else
+                hv[0][i] = half_down(bx.mn.x); hv[1][i] = half_down(bx.mn.y); hv[2][i] = half_down(bx.mn.z);
+                hv[3][i] = half_up(bx.mx.x); hv[4][i] = half_up(bx.mx.y); hv[5][i] = half_up(bx.mx.z);
+#endif
+                if (used && !slots[si].cone.open()) {
+                    // The device culls the child when |dn . axis| < threshold, dn = normalised ray direction, all in
+                    // half precision: the axis components round to nearest (error <= 8.7e-4 in the dot product), dn
+                    // likewise, three half products / sums add <= 2.5e-3; the threshold gives 8e-3 away and is
+                    // rounded down.  A threshold that ends up <= 0 leaves the child unrestricted.
+                    const Cone& c = slots[si].cone;
+                    const double thr = std::cos(std::min(c.alpha + 2e-3, 1.5707963)) - 8e-3;
+                    if (thr > 0) {
+                        cv[0][i] = half_bits_rn((float)c.ax); cv[1][i] = half_bits_rn((float)c.ay); cv[2][i] = half_bits_rn((float)c.az);
+                        cv[3][i] = half_down((float)thr);
+                        if (cv[3][i] & 0x8000u) cv[3][i] = 0;
+                    }
+                }
+                refs[i] = IREF_NONE;
+                if (used) refs[i] = (slots[si].ref & IREF_LEAF) ? slots[si].ref : emit(slots[si].ref, depth + 1);
             }
-            uint32_t ref = IREF_NONE;
-            if (used) ref = (slots[i].ref & IREF_LEAF) ? slots[i].ref : emit(slots[i].ref, depth + 1);
-            f4 q0{centre[0], centre[1], centre[2], 0.f};
-            const uint32_t hxy = (uint32_t)half[0] | ((uint32_t)half[1] << 16);
-            std::memcpy(&q0.w, &hxy, 4);
-            out[kIndexNodeF4 * me + kIndexChildF4 * i] = q0;
-            out[kIndexNodeF4 * me + kIndexChildF4 * i + 1] = bits4((uint32_t)half[2] | ((uint32_t)thr16 << 16),
-                                                                   (uint32_t)axis[0] | ((uint32_t)axis[1] << 16), (uint32_t)axis[2], ref);
+            uint32_t w[16];
+            for (int r = 0; r < 6; ++r) {
+                w[2 * r] = (uint32_t)hv[r][0] | ((uint32_t)hv[r][1] << 16);
+                w[2 * r + 1] = (uint32_t)hv[r][2] | ((uint32_t)hv[r][3] << 16);
+            }
+            for (int i = 0; i < 4; ++i) w[12 + i] = refs[i];
+            for (int q = 0; q < 4; ++q) out[kIndexNodeF4 * me + kIndexBlockF4 * blk + q] = bits4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+#if RTC_NODE_CONES
+            // q4 = axis.x[0..3] axis.y[0..3] ; q5 = axis.z[0..3] threshold[0..3]  (halves, two children per word)
+            uint32_t cw[8];
+            for (int r = 0; r < 4; ++r) {
+                cw[2 * r] = (uint32_t)cv[r][0] | ((uint32_t)cv[r][1] << 16);
+                cw[2 * r + 1] = (uint32_t)cv[r][2] | ((uint32_t)cv[r][3] << 16);
+            }
+            out[kIndexNodeF4 * me + kIndexBlockF4 * blk + 4] = bits4(cw[0], cw[1], cw[2], cw[3]);
+            out[kIndexNodeF4 * me + kIndexBlockF4 * blk + 5] = bits4(cw[4], cw[5], cw[6], cw[7]);
+#endif
         }
         return me;
     }

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -61,49 +62,80 @@ constexpr int kMaxWhittedDepth = 32;   // course_device.cuh kWhittedStack = kMax
 }  // namespace
 
 struct rtc_scene {
-    HostScene host;
+    // the host scene is shared by the per-device replicas of a multi-device render (rtc_render_u8_multi)
+    std::shared_ptr<HostScene> host_ptr;
+    HostScene& host;
+    rtc_scene() : host_ptr(std::make_shared<HostScene>()), host(*host_ptr) {}
+    explicit rtc_scene(const std::shared_ptr<HostScene>& h) : host_ptr(h), host(*h) {}
     int device = -1;
     int sms = 0;
     int traversal = RTC_TRAVERSAL_INDEX;
     uint64_t batch_paths = kDefaultBatchPaths;
     uint64_t device_bytes = 0;
-    // scene arrays in HBM
-    // one device arena + one pinned host mirror: a scene upload is a single H2D copy
-    unsigned char* arena_dev = nullptr;
+    // scene arrays in HBM: one pinned host mirror, TWO device arenas.  A scene upload is a single H2D copy;
+    // rtc_scene_upload_async fills the arena that is not in use on a copy stream of its own, so that the upload of
+    // frame i + 1 runs under the kernels of frame i, and the next render switches over.
+    unsigned char* arena_dev[2] = {nullptr, nullptr};
     unsigned char* arena_host = nullptr;  // cudaMallocHost
     size_t arena_bytes = 0;
-    DevScene slices{};                    // pointers into arena_dev (scalars filled by dev())
+    size_t part_off[16] = {0};            // offsets of the scene arrays inside an arena
+    int arena_cur = 0;                    // the arena the next render reads
+    DevScene slices{};                    // pointers into arena_dev[arena_cur] (scalars filled by dev())
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t arena_ready[2] = {nullptr, nullptr};  // upload into arena i complete
+    cudaEvent_t arena_idle[2] = {nullptr, nullptr};   // last render that read arena i complete
+    bool arena_pending = false;                        // an async upload has to be waited for by the next render
+    // frames in flight (rtc_frame_begin / rtc_frame_end): per slot a stream, buffers and a pinned image
+    struct Frame {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf<float> accum;
+        DevBuf<uint8_t> rgb;
+        uint8_t* host = nullptr;   // cudaMallocHost
+        size_t host_bytes = 0;
+        bool busy = false;
+    };
+    Frame frames[2];
+    // float4 pixel sums of the renders in flight (k_shade deposits, k_fold reads): two, used alternately
+    DevBuf<float4> accum4[2];
+    cudaEvent_t accum4_idle[2] = {nullptr, nullptr};
+    int accum4_next = 0;
+    // probe entry points (rtc_intersect, ...): staging buffers that only ever grow
+    struct Probe {
+        DevBuf<float> fin[3];
+        DevBuf<float> fout[2];
+        DevBuf<int32_t> iout[2];
+        DevBuf<float4> ray[2];
+        DevBuf<uint32_t> hit, tq, q;
+    } probe;
+    // per-device replicas for rtc_render_u8_multi (this scene's own device is not among them)
+    std::vector<rtc_scene*> replicas;
+    cudaStream_t multi_stream = nullptr;
+    cudaEvent_t multi_done = nullptr;
     // wavefront state: kMaxLanes independent sets, each with its own stream, so that batches
     // overlap (the tail of one persistent k_traverse launch runs next to the other lane's kernels)
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        bool l2_window_set = false;
         DevBuf<float4> path[2][3];           // two ping-pong sets of (origin | sample, direction | closest plane, throughput | pixel)
         DevBuf<uint32_t> hit_id[2];
         DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
-        DevBuf<unsigned char> recpool;       // k_traverse_pool: leaf-hit records of the rays resident in its warps
         DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
         void release() {
             for (auto& set : path) for (auto& b : set) b.release();
             for (auto& b : hit_id) b.release();
-            trav_queue.release(); queue.release(); recpool.release();
+            trav_queue.release(); queue.release();
             if (done) cudaEventDestroy(done);
             if (stream) cudaStreamDestroy(stream);
             done = nullptr; stream = nullptr;
-            l2_window_set = false;
         }
     };
     static constexpr int kMaxLanes = 4;
     Lane lanes[kMaxLanes];
     int nlanes = 2;                      // env RTC_STREAMS (1..4)
-    bool l2_persist = false;             // env RTC_L2_PERSIST: pin the scene arena in L2 (access-policy window per lane)
-    size_t l2_window_bytes = 0;
-    size_t prop_persist_max = 0, prop_window_max = 0;
     cudaEvent_t fork = nullptr;
     DevBuf<unsigned long long> stats;    // 16 words: rtc_render_counters (8) + rtc_traverse_lanes (8)
     DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
-    DevBuf<float4> accum4;               // per-pixel float4 sums of the frame being rendered (k_shade deposits, k_fold reads)
     DevBuf<uint8_t> rgb;
     uint64_t launches = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -155,14 +187,42 @@ struct rtc_scene {
         return S;
     }
     void release_device() {
-        if (arena_dev) cudaFree(arena_dev);
+        for (rtc_scene* r : replicas) {
+            cudaSetDevice(r->device);
+            r->release_device();
+            delete r;
+        }
+        replicas.clear();
+        if (device >= 0) cudaSetDevice(device);
+        for (auto& a : arena_dev) { if (a) cudaFree(a); a = nullptr; }
         if (arena_host) cudaFreeHost(arena_host);
-        arena_dev = arena_host = nullptr;
+        arena_host = nullptr;
         arena_bytes = 0;
         for (auto& l : lanes) l.release();
+        for (auto& f : frames) {
+            if (f.stream) cudaStreamDestroy(f.stream);
+            if (f.done) cudaEventDestroy(f.done);
+            if (f.host) cudaFreeHost(f.host);
+            f.accum.release(); f.rgb.release();
+            f = Frame();
+        }
+        for (auto& e : arena_ready) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : arena_idle) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : accum4_idle) { if (e) cudaEventDestroy(e); e = nullptr; }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (multi_stream) cudaStreamDestroy(multi_stream);
+        if (multi_done) cudaEventDestroy(multi_done);
+        copy_stream = multi_stream = nullptr;
+        multi_done = nullptr;
         if (fork) cudaEventDestroy(fork);
         fork = nullptr;
-        stats.release(); accum.release(); accum4.release(); rgb.release();
+        stats.release(); accum.release(); rgb.release();
+        for (auto& b : accum4) b.release();
+        for (auto& b : probe.fin) b.release();
+        for (auto& b : probe.fout) b.release();
+        for (auto& b : probe.iout) b.release();
+        for (auto& b : probe.ray) b.release();
+        probe.hit.release(); probe.tq.release(); probe.q.release();
         collect_spans();
         for (cudaEvent_t e : event_pool) cudaEventDestroy(e);
         event_pool.clear();
@@ -171,68 +231,109 @@ struct rtc_scene {
 
 namespace {
 
-// Lays the flat scene arrays out in one arena (256-byte aligned slices).  First call: allocates
-// the device arena and its pinned host mirror and fills the mirror; every call: ONE async H2D copy.
-int upload_scene(rtc_scene* s, uint64_t* h2d) {
+// Lays the flat scene arrays out in one arena (256-byte aligned slices).  First call: allocates the device arena
+// and its pinned host mirror and fills the mirror.
+void point_slices(rtc_scene* s, int which) {
+    unsigned char* base = s->arena_dev[which];
+    const size_t* off = s->part_off;
+    DevScene& D = s->slices;
+    D.geo0 = (const float4*)(base + off[0]);   D.geo1 = (const float4*)(base + off[1]);
+    D.geo2 = (const float4*)(base + off[2]);   D.xf_pos = (const float4*)(base + off[3]);
+    D.xf_rot = (const float4*)(base + off[4]); D.mat0 = (const float4*)(base + off[5]);
+    D.mat1 = (const float4*)(base + off[6]);   D.inodes = (const float4*)(base + off[7]);
+    D.rnodes = (const float4*)(base + off[8]); D.rmeta = (const uint4*)(base + off[9]);
+    D.lca = (const uint32_t*)(base + off[10]); D.lights = (const int32_t*)(base + off[11]);
+    D.planes = (const float4*)(base + off[12]);
+    D.ubox = (const float4*)(base + off[13]);
+    D.plights = (const float4*)(base + off[14]);
+    s->arena_cur = which;
+}
+int prepare_arena(rtc_scene* s) {
     if (s->device < 0) return fail(RTC_ERR_NO_DEVICE, "scene has no CUDA device");
     CU(cudaSetDevice(s->device));
+    if (s->arena_host) return RTC_OK;
     const FlatScene& F = s->host.flat;
-    struct Part { const void* src; size_t bytes; size_t off; };
-    Part parts[] = {
-        {F.geo0.data(), F.geo0.size() * sizeof(f4), 0},     {F.geo1.data(), F.geo1.size() * sizeof(f4), 0},
-        {F.geo2.data(), F.geo2.size() * sizeof(f4), 0},     {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4), 0},
-        {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4), 0}, {F.mat0.data(), F.mat0.size() * sizeof(f4), 0},
-        {F.mat1.data(), F.mat1.size() * sizeof(f4), 0},     {F.inodes.data(), F.inodes.size() * sizeof(f4), 0},
-        {F.rnodes.data(), F.rnodes.size() * sizeof(f4), 0}, {F.rmeta.data(), F.rmeta.size() * sizeof(u4), 0},
-        {F.lca.data(), F.lca.size() * sizeof(uint32_t), 0}, {F.lights.data(), F.lights.size() * sizeof(int32_t), 0},
-        {F.planes.data(), F.planes.size() * sizeof(f4), 0}, {F.ubox.data(), F.ubox.size() * sizeof(f4), 0},
-        {F.plights.data(), F.plights.size() * sizeof(f4), 0},
+    struct Part { const void* src; size_t bytes; };
+    const Part parts[] = {
+        {F.geo0.data(), F.geo0.size() * sizeof(f4)},     {F.geo1.data(), F.geo1.size() * sizeof(f4)},
+        {F.geo2.data(), F.geo2.size() * sizeof(f4)},     {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4)},
+        {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4)}, {F.mat0.data(), F.mat0.size() * sizeof(f4)},
+        {F.mat1.data(), F.mat1.size() * sizeof(f4)},     {F.inodes.data(), F.inodes.size() * sizeof(f4)},
+        {F.rnodes.data(), F.rnodes.size() * sizeof(f4)}, {F.rmeta.data(), F.rmeta.size() * sizeof(u4)},
+        {F.lca.data(), F.lca.size() * sizeof(uint32_t)}, {F.lights.data(), F.lights.size() * sizeof(int32_t)},
+        {F.planes.data(), F.planes.size() * sizeof(f4)}, {F.ubox.data(), F.ubox.size() * sizeof(f4)},
+        {F.plights.data(), F.plights.size() * sizeof(f4)},
     };
     size_t total = 0, payload = 0;
-    for (Part& p : parts) {
-        p.off = total;
+    int i = 0;
+    for (const Part& p : parts) {
+        s->part_off[i++] = total;
         total += (p.bytes + 255) & ~(size_t)255;
         payload += p.bytes;
     }
     if (total == 0) total = 256;
-    if (!s->arena_dev) {
-        CU(cudaMalloc(&s->arena_dev, total));
-        CU(cudaMallocHost(&s->arena_host, total));
-        std::memset(s->arena_host, 0, total);
-        for (const Part& p : parts)
-            if (p.bytes) std::memcpy(s->arena_host + p.off, p.src, p.bytes);
-        s->arena_bytes = total;
-        unsigned char* base = s->arena_dev;
-        DevScene& D = s->slices;
-        D.geo0 = (const float4*)(base + parts[0].off);   D.geo1 = (const float4*)(base + parts[1].off);
-        D.geo2 = (const float4*)(base + parts[2].off);   D.xf_pos = (const float4*)(base + parts[3].off);
-        D.xf_rot = (const float4*)(base + parts[4].off); D.mat0 = (const float4*)(base + parts[5].off);
-        D.mat1 = (const float4*)(base + parts[6].off);   D.inodes = (const float4*)(base + parts[7].off);
-        D.rnodes = (const float4*)(base + parts[8].off); D.rmeta = (const uint4*)(base + parts[9].off);
-        D.lca = (const uint32_t*)(base + parts[10].off); D.lights = (const int32_t*)(base + parts[11].off);
-        D.planes = (const float4*)(base + parts[12].off);
-        D.ubox = (const float4*)(base + parts[13].off);
-        D.plights = (const float4*)(base + parts[14].off);
+    CU(cudaMalloc(&s->arena_dev[0], total));
+    CU(cudaMallocHost(&s->arena_host, total));
+    std::memset(s->arena_host, 0, total);
+    i = 0;
+    for (const Part& p : parts) {
+        if (p.bytes) std::memcpy(s->arena_host + s->part_off[i], p.src, p.bytes);
+        ++i;
     }
-    CU(cudaMemcpyAsync(s->arena_dev, s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, nullptr));
-    CU(cudaStreamSynchronize(nullptr));
-    const uint64_t bytes = payload;
-    if (const char* v = std::getenv("RTC_L2_PERSIST")) {
-        if (std::atoi(v) > 0 && s->prop_persist_max > 0 && !s->l2_persist) {
-            size_t want = s->arena_bytes + (s->arena_bytes >> 2);
-            if (want > s->prop_persist_max) want = s->prop_persist_max;
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-                s->l2_persist = true;
-                s->l2_window_bytes = s->arena_bytes < s->prop_window_max ? s->arena_bytes : s->prop_window_max;
-            } else cudaGetLastError();
-        }
+    s->arena_bytes = total;
+    s->device_bytes = payload;
+    point_slices(s, 0);
+    for (int a = 0; a < 2; ++a) {
+        CU(cudaEventCreateWithFlags(&s->arena_ready[a], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->arena_idle[a], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->accum4_idle[a], cudaEventDisableTiming));
     }
-    if (!s->stats.p) {
-        CU(s->stats.ensure(kStatWords));
-        CU(cudaMemset(s->stats.p, 0, kStatWords * sizeof(unsigned long long)));
+    CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CU(s->stats.ensure(kStatWords));
+    CU(cudaMemset(s->stats.p, 0, kStatWords * sizeof(unsigned long long)));
+    return RTC_OK;
+}
+// synchronous upload into the arena in use: ONE H2D copy, complete on return
+int upload_scene(rtc_scene* s, uint64_t* h2d) {
+    int rc = prepare_arena(s);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());   // nothing may still be reading the arena
+    CU(cudaMemcpyAsync(s->arena_dev[s->arena_cur], s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, s->copy_stream));
+    CU(cudaStreamSynchronize(s->copy_stream));
+    s->arena_pending = false;
+    if (h2d) *h2d = s->device_bytes;
+    return RTC_OK;
+}
+// asynchronous upload into the OTHER arena on the copy stream; the next render waits for it and reads that arena
+int upload_scene_async(rtc_scene* s, uint64_t* h2d) {
+    int rc = prepare_arena(s);
+    if (rc) return rc;
+    const int target = 1 - s->arena_cur;
+    if (!s->arena_dev[target]) CU(cudaMalloc(&s->arena_dev[target], s->arena_bytes));
+    CU(cudaStreamWaitEvent(s->copy_stream, s->arena_idle[target], 0));   // the renders that read it are done
+    CU(cudaMemcpyAsync(s->arena_dev[target], s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, s->copy_stream));
+    CU(cudaEventRecord(s->arena_ready[target], s->copy_stream));
+    point_slices(s, target);
+    s->arena_pending = true;
+    if (h2d) *h2d = s->device_bytes;
+    return RTC_OK;
+}
+
+int finish_scene(rtc_scene* s, int device) {
+    if (const char* v = std::getenv("RTC_STREAMS")) {
+        int n = std::atoi(v);
+        s->nlanes = n < 1 ? 1 : (n > rtc_scene::kMaxLanes ? rtc_scene::kMaxLanes : n);
     }
-    s->device_bytes = bytes;
-    if (h2d) *h2d = bytes;
+    s->device = device;
+    if (device >= 0) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count)
+            return fail(RTC_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " is not available");
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, device);
+        s->sms = prop.multiProcessorCount;
+        return upload_scene(s, nullptr);
+    }
     return RTC_OK;
 }
 
@@ -266,28 +367,10 @@ rtc_scene* make_scene(const std::string& text, int device, int dialect = DIALECT
         delete s;
         return nullptr;
     }
-    if (const char* v = std::getenv("RTC_STREAMS")) {
-        int n = std::atoi(v);
-        s->nlanes = n < 1 ? 1 : (n > rtc_scene::kMaxLanes ? rtc_scene::kMaxLanes : n);
-    }
-    s->device = device;
-    if (device >= 0) {
-        int count = 0;
-        if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) {
-            fail(RTC_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " is not available");
-            delete s;
-            return nullptr;
-        }
-        cudaDeviceProp prop;
-        cudaGetDeviceProperties(&prop, device);
-        s->sms = prop.multiProcessorCount;
-        s->prop_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-        s->prop_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-        if (upload_scene(s, nullptr) != RTC_OK) {
-            s->release_device();
-            delete s;
-            return nullptr;
-        }
+    if (finish_scene(s, device) != RTC_OK) {
+        if (device >= 0) s->release_device();
+        delete s;
+        return nullptr;
     }
     return s;
 }
@@ -339,23 +422,9 @@ int ensure_wavefront(rtc_scene* s, uint64_t cap, int nlanes) {
         rtc_scene::Lane& l = s->lanes[i];
         if (!l.stream) CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         if (!l.done) CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-        if (s->l2_persist && !l.l2_window_set) {
-            // the scene arena (BVH nodes, triangles: what k_traverse gathers from) stays in L2 while the wavefront
-            // state streams through it
-            cudaStreamAttrValue attr;
-            std::memset(&attr, 0, sizeof attr);
-            attr.accessPolicyWindow.base_ptr = s->arena_dev;
-            attr.accessPolicyWindow.num_bytes = s->l2_window_bytes;
-            attr.accessPolicyWindow.hitRatio = 1.0f;
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            CU(cudaStreamSetAttribute(l.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-            l.l2_window_set = true;
-        }
         for (auto& set : l.path) for (auto& b : set) CU(b.ensure(cap));
         for (auto& b : l.hit_id) CU(b.ensure(cap));
         CU(l.trav_queue.ensure(cap));
-        CU(l.recpool.ensure(traverse_pool_record_bytes(s->sms)));
         CU(l.queue.ensure(3 * kMaxDepthSlots));
     }
     return RTC_OK;
@@ -465,43 +534,61 @@ int rtc_set_batch_paths(rtc_scene* s, uint64_t paths) {
 }
 
 // ------------------------------------------------------------------ probes (host buffers)
-int rtc_intersect(const rtc_scene* s, long n, const float* o, const float* d, int32_t* id, float* t, float* normal,
+// Scene::RayIntersection for a batch of rays whose arrays are ALREADY on the scene's device (3 floats per origin /
+// direction / normal): the kernels of the render path on pooled scratch buffers, asynchronous on `stream`.
+int rtc_intersect_dev(rtc_scene* s, long n, const float* o_dev, const float* d_dev, int32_t* id_dev, float* t_dev,
+                      float* normal_dev, int32_t* interior_dev, int mode, void* stream) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (n < 0 || !o_dev || !d_dev || !id_dev || !t_dev || !normal_dev || !interior_dev) return fail(RTC_ERR_ARG, "bad argument");
+    if (n == 0) return RTC_OK;
+    if ((uint64_t)n > (1ull << 28)) return fail(RTC_ERR_ARG, "too many rays in one call (limit 2^28)");
+    rtc_scene::Probe& pb = s->probe;
+    CU(pb.ray[0].ensure((size_t)n)); CU(pb.ray[1].ensure((size_t)n));
+    CU(pb.hit.ensure((size_t)n)); CU(pb.tq.ensure((size_t)n)); CU(pb.q.ensure(4));
+    cudaStream_t st = (cudaStream_t)stream;
+    PathSoA P{pb.ray[0].p, pb.ray[1].p, nullptr};
+    HitSoA H{pb.hit.p};
+    uint32_t* q = pb.q.p;
+    CU(cudaMemsetAsync(q, 0, 4 * sizeof(uint32_t), st));
+    if (s->arena_pending) CU(cudaStreamWaitEvent(st, s->arena_ready[s->arena_cur], 0));
+    LaunchCtx c{st, s->sms};
+    DevScene S = s->dev();
+    // the same kernels as the render path: rays into the float4 queue layout, extend, read back
+    launch_pack_rays(c, n, o_dev, d_dev, P, q);
+    if (mode == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, P, H, q, (uint32_t)n);
+    else {
+        launch_pre(c, S, P, H, q, (uint32_t)n, pb.tq.p, q + 1);
+        launch_traverse(c, S, P, H, (uint32_t)n, pb.tq.p, q + 1, q + 2, false, s->stats.p);
+    }
+    launch_unpack_hits(c, S, n, P, H, id_dev, t_dev, normal_dev, interior_dev);
+    CU(cudaEventRecord(s->arena_idle[s->arena_cur], st));
+    CU(cudaGetLastError());
+    return RTC_OK;
+}
+// host-buffer form: two copies in, one kernel chain, four copies out, on buffers that are allocated once and grow
+int rtc_intersect(const rtc_scene* cs, long n, const float* o, const float* d, int32_t* id, float* t, float* normal,
                   int32_t* interior, int mode) {
+    rtc_scene* s = const_cast<rtc_scene*>(cs);
     int rc = need_device(s);
     if (rc) return rc;
     if (n < 0 || !o || !d || !id || !t || !normal || !interior) return fail(RTC_ERR_ARG, "bad argument");
     if (n == 0) return RTC_OK;
     if ((uint64_t)n > (1ull << 28)) return fail(RTC_ERR_ARG, "too many rays in one call (limit 2^28)");
-    Staged st;
-    float* od = st.in(o, 3 * (size_t)n); NEED(od);
-    float* dd = st.in(d, 3 * (size_t)n); NEED(dd);
-    int32_t* idd = st.out<int32_t>((size_t)n); NEED(idd);
-    float* td = st.out<float>((size_t)n); NEED(td);
-    float* nd = st.out<float>(3 * (size_t)n); NEED(nd);
-    int32_t* ind = st.out<int32_t>((size_t)n); NEED(ind);
-    // the same kernels as the render path: rays into the float4 queue layout, extend, read back
-    PathSoA P{st.out<float4>((size_t)n), st.out<float4>((size_t)n), nullptr};
-    NEED(P.o); NEED(P.d);
-    HitSoA H{st.out<uint32_t>((size_t)n)};
-    NEED(H.id);
-    uint32_t* tq = st.out<uint32_t>((size_t)n); NEED(tq);
-    uint32_t* q = st.out<uint32_t>(4); NEED(q);
-    CU(cudaMemset(q, 0, 4 * sizeof(uint32_t)));
-    LaunchCtx c{nullptr, s->sms};
-    DevScene S = s->dev();
-    launch_pack_rays(c, n, od, dd, P, q);
-    if (mode == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, P, H, q, (uint32_t)n);
-    else {
-        launch_pre(c, S, P, H, q, (uint32_t)n, tq, q + 1);
-        unsigned char* recpool = st.out<unsigned char>(traverse_pool_record_bytes(s->sms)); NEED(recpool);
-        launch_traverse(c, S, P, H, (uint32_t)n, tq, q + 1, q + 2, false, s->stats.p, recpool);
-    }
-    launch_unpack_hits(c, S, n, P, H, idd, td, nd, ind);
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(id, idd, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(t, td, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(normal, nd, (size_t)n * 12, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(interior, ind, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    rtc_scene::Probe& pb = s->probe;
+    const size_t N = (size_t)n;
+    CU(pb.fin[0].ensure(3 * N)); CU(pb.fin[1].ensure(3 * N));
+    CU(pb.fout[0].ensure(N)); CU(pb.fout[1].ensure(3 * N));
+    CU(pb.iout[0].ensure(N)); CU(pb.iout[1].ensure(N));
+    CU(cudaMemcpyAsync(pb.fin[0].p, o, 3 * N * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+    CU(cudaMemcpyAsync(pb.fin[1].p, d, 3 * N * sizeof(float), cudaMemcpyHostToDevice, nullptr));
+    if ((rc = rtc_intersect_dev(s, n, pb.fin[0].p, pb.fin[1].p, pb.iout[0].p, pb.fout[0].p, pb.fout[1].p, pb.iout[1].p, mode, nullptr)))
+        return rc;
+    CU(cudaMemcpyAsync(id, pb.iout[0].p, N * 4, cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaMemcpyAsync(t, pb.fout[0].p, N * 4, cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaMemcpyAsync(normal, pb.fout[1].p, N * 12, cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaMemcpyAsync(interior, pb.iout[1].p, N * 4, cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
     return RTC_OK;
 }
 int rtc_primitive_intersect(const rtc_scene* s, int prim, long n, const float* o, const float* d, int32_t* hit, float* t,
@@ -603,10 +690,12 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         // hw1 / hw2: ONE deterministic frame = sample 0.  A range that holds sample 0 adds the colour once, any
         // other range adds nothing, so that sample ranges split over several devices still sum to one frame.
         if (sample_begin > 0) return RTC_OK;
+        if (s->arena_pending) CU(cudaStreamWaitEvent((cudaStream_t)stream, s->arena_ready[s->arena_cur], 0));
         LaunchCtx c{(cudaStream_t)stream, s->sms};
         if (s->host.dialect == DIALECT_HW1) launch_raycast_hw1(c, s->dev(), accum_dev);
         else launch_whitted_hw2(c, s->dev(), accum_dev);
         s->launches++;
+        CU(cudaEventRecord(s->arena_idle[s->arena_cur], (cudaStream_t)stream));
         CU(cudaGetLastError());
         return RTC_OK;
     }
@@ -623,8 +712,17 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     const int nlanes = s->profiling ? 1 : (int)(nbatches < (uint64_t)s->nlanes ? nbatches : (uint64_t)s->nlanes);
     if ((rc = ensure_wavefront(s, cap, nlanes))) return rc;
     cudaStream_t user = (cudaStream_t)stream;
-    CU(s->accum4.ensure(npix));
-    CU(cudaMemsetAsync(s->accum4.p, 0, npix * sizeof(float4), user));
+    // the float4 pixel sums of this render: two buffers used alternately, so that two renders may be in flight on
+    // two streams; a third waits for the first to have been folded
+    const int a4 = s->accum4_next;
+    s->accum4_next ^= 1;
+    DevBuf<float4>& accum4 = s->accum4[a4];
+    CU(accum4.ensure(npix));
+    CU(cudaStreamWaitEvent(user, s->accum4_idle[a4], 0));
+    CU(cudaMemsetAsync(accum4.p, 0, npix * sizeof(float4), user));
+    // an asynchronous scene upload (rtc_scene_upload_async) has to have landed before the first kernel reads it
+    const int arena = s->arena_cur;
+    if (s->arena_pending) CU(cudaStreamWaitEvent(user, s->arena_ready[arena], 0));
     DevScene S = s->dev();
     // fork: the lane streams start after everything already queued on the caller's stream
     CU(cudaEventRecord(s->fork, user));
@@ -648,12 +746,11 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         for (uint32_t b = 1; b <= depth; ++b) {
             s->span_begin(1, st);
             if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, L.queue.p + (b - 1), count);
-            else launch_traverse(c, S, cur, hcur, count, L.trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p,
-                                 L.recpool.p);
+            else launch_traverse(c, S, cur, hcur, count, L.trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
             s->span_end(st);
             s->span_begin(2, st);
             launch_shade(c, S, cur, hcur, nxt, hnxt, L.queue.p + (b - 1), L.queue.p + b, L.trav_queue.p, tqc + b, count,
-                         s->accum4.p, b, seed);
+                         accum4.p, b, seed);
             s->span_end(st);
             s->launches += 2;
             PathSoA tmp = cur; cur = nxt; nxt = tmp;
@@ -667,8 +764,10 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         CU(cudaEventRecord(s->lanes[i].done, s->lanes[i].stream));
         CU(cudaStreamWaitEvent(user, s->lanes[i].done, 0));
     }
-    launch_fold(LaunchCtx{user, s->sms}, s->accum4.p, accum_dev, (uint32_t)npix);
+    launch_fold(LaunchCtx{user, s->sms}, accum4.p, accum_dev, (uint32_t)npix);
     s->launches++;
+    CU(cudaEventRecord(s->accum4_idle[a4], user));
+    CU(cudaEventRecord(s->arena_idle[arena], user));
     CU(cudaGetLastError());
     return RTC_OK;
 }
@@ -747,6 +846,210 @@ int rtc_render_ppm(rtc_scene* s, uint32_t seed, const char* out_path) {
     size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
     std::vector<uint8_t> img(nvalues);
     int rc = rtc_render_u8(s, seed, img.data());
+    if (rc) return rc;
+    std::ofstream out(out_path, std::ios::binary);
+    if (!out) return fail(RTC_ERR_IO, std::string("cannot open output file ") + out_path);
+    out << "P6\n" << s->host.cam.width << " " << s->host.cam.height << "\n" << 255 << "\n";  // src/scene.cpp:206-208
+    out.write(reinterpret_cast<const char*>(img.data()), (std::streamsize)img.size());
+    if (!out) return fail(RTC_ERR_IO, std::string("write failed: ") + out_path);
+    return RTC_OK;
+}
+
+int rtc_scene_upload_async(rtc_scene* s, uint64_t* h2d_bytes) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    return upload_scene_async(s, h2d_bytes);
+}
+
+// ------------------------------------------------------------------ frames in flight
+// One frame = what run.sh does with a scene that is already parsed: flattened scene host -> HBM, render, resolve,
+// 8-bit image HBM -> host.  rtc_frame_begin queues all of it (no host synchronisation: the upload on the copy stream
+// into the arena that is not being read, the kernels on the slot's stream, the image into a pinned buffer),
+// rtc_frame_end waits for the slot and hands the image over.  Two slots: frame i + 1 is queued before frame i is collected.
+int rtc_frame_begin(rtc_scene* s, uint32_t seed, int slot, uint64_t* h2d_bytes) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (slot < 0 || slot > 1) return fail(RTC_ERR_ARG, "frame slot must be 0 or 1");
+    rtc_scene::Frame& f = s->frames[slot];
+    if (f.busy) return fail(RTC_ERR_ARG, "frame slot is in flight: call rtc_frame_end first");
+    const uint32_t samples = s->host.dialect <= DIALECT_HW2 ? 1u : s->host.samples;
+    if (samples == 0) return fail(RTC_ERR_ARG, "scene has SAMPLES 0");
+    const size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (!f.stream) CU(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+    if (!f.done) CU(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    CU(f.accum.ensure(nvalues));
+    CU(f.rgb.ensure(nvalues));
+    if (f.host_bytes < nvalues) {
+        if (f.host) cudaFreeHost(f.host);
+        f.host = nullptr; f.host_bytes = 0;
+        CU(cudaMallocHost(&f.host, nvalues ? nvalues : 1));
+        f.host_bytes = nvalues;
+    }
+    if ((rc = upload_scene_async(s, h2d_bytes))) return rc;
+    if (nvalues) {
+        CU(cudaMemsetAsync(f.accum.p, 0, nvalues * sizeof(float), f.stream));
+        if ((rc = rtc_render_accumulate(s, seed, 0, samples, f.accum.p, f.stream))) return rc;
+        if ((rc = rtc_render_resolve(s, f.accum.p, samples, f.rgb.p, f.stream))) return rc;
+        CU(cudaMemcpyAsync(f.host, f.rgb.p, nvalues, cudaMemcpyDeviceToHost, f.stream));
+    }
+    CU(cudaEventRecord(f.done, f.stream));
+    f.busy = true;
+    return RTC_OK;
+}
+int rtc_frame_end(rtc_scene* s, int slot, uint8_t* rgb_host) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (slot < 0 || slot > 1) return fail(RTC_ERR_ARG, "frame slot must be 0 or 1");
+    rtc_scene::Frame& f = s->frames[slot];
+    if (!f.busy) return fail(RTC_ERR_ARG, "frame slot is not in flight");
+    CU(cudaEventSynchronize(f.done));
+    f.busy = false;
+    const size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (rgb_host && nvalues) std::memcpy(rgb_host, f.host, nvalues);
+    return RTC_OK;
+}
+// resolve a device accumulation buffer and start the 8-bit image on its way to a pinned host buffer (slot 0's);
+// rtc_host_image_wait collects the last one.  Used by multi-process renders after their reduce.
+int rtc_resolve_to_host_async(rtc_scene* s, const float* accum_dev, uint32_t total_samples, void* stream) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    rtc_scene::Frame& f = s->frames[0];
+    const size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (!accum_dev || nvalues == 0) return fail(RTC_ERR_ARG, "bad argument");
+    if (!f.stream) CU(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+    if (!f.done) CU(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    CU(f.rgb.ensure(nvalues));
+    if (f.host_bytes < nvalues) {
+        if (f.host) cudaFreeHost(f.host);
+        f.host = nullptr; f.host_bytes = 0;
+        CU(cudaMallocHost(&f.host, nvalues));
+        f.host_bytes = nvalues;
+    }
+    cudaStream_t user = (cudaStream_t)stream;
+    // the previous image must have left the device buffer before it is resolved into again
+    CU(cudaStreamWaitEvent(user, f.done, 0));
+    if ((rc = rtc_render_resolve(s, accum_dev, total_samples, f.rgb.p, user))) return rc;
+    if (!s->fork) CU(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(s->fork, user));
+    CU(cudaStreamWaitEvent(f.stream, s->fork, 0));
+    CU(cudaMemcpyAsync(f.host, f.rgb.p, nvalues, cudaMemcpyDeviceToHost, f.stream));
+    CU(cudaEventRecord(f.done, f.stream));
+    return RTC_OK;
+}
+int rtc_host_image_wait(rtc_scene* s, uint8_t* rgb_host) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    rtc_scene::Frame& f = s->frames[0];
+    if (!f.done) return fail(RTC_ERR_ARG, "no image in flight");
+    CU(cudaEventSynchronize(f.done));
+    const size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (rgb_host && nvalues) std::memcpy(rgb_host, f.host, nvalues);
+    return RTC_OK;
+}
+
+// ------------------------------------------------------------------ one call, several devices
+// Scene::Render uses the whole machine (src/scene.cpp:212 omp_set_num_threads(hardware_concurrency)); so does this:
+// the samples are split over `ndev` devices of this process (disjoint Philox streams, rtc_render_accumulate), every
+// device renders into its own buffer, and the first device sums them over NVLink peer access and resolves
+// (k_resolve_peers).  A device may be listed more than once (its share is then rendered twice as often).
+namespace {
+rtc_scene* replica_on(rtc_scene* s, int device, int ordinal) {
+    // the ordinal-th use of `device` in the list: the scene itself serves the first use of its own device
+    int seen = 0;
+    if (device == s->device) { if (ordinal == 0) return s; seen = 1; }
+    for (rtc_scene* r : s->replicas)
+        if (r->device == device) { if (seen == ordinal) return r; ++seen; }
+    rtc_scene* r = new rtc_scene(s->host_ptr);
+    r->traversal = s->traversal;
+    r->batch_paths = s->batch_paths;
+    if (finish_scene(r, device) != RTC_OK) {
+        r->release_device();
+        delete r;
+        return nullptr;
+    }
+    s->replicas.push_back(r);
+    return r;
+}
+}  // namespace
+int rtc_render_u8_multi(rtc_scene* s, const int* devices, int ndev, uint32_t seed, uint8_t* rgb_host, float* sum_host) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!devices || ndev < 1 || ndev > kMaxPeers || !rgb_host) return fail(RTC_ERR_ARG, "bad argument");
+    const uint32_t samples = s->host.dialect <= DIALECT_HW2 ? 1u : s->host.samples;
+    if (samples == 0) return fail(RTC_ERR_ARG, "scene has SAMPLES 0");
+    const size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    if (nvalues == 0) return RTC_OK;
+    // the first listed device reduces: make it this scene's device or a replica there
+    std::vector<rtc_scene*> ctx((size_t)ndev, nullptr);
+    std::vector<int> uses(64, 0);
+    for (int i = 0; i < ndev; ++i) {
+        if (devices[i] < 0 || devices[i] >= 64) return fail(RTC_ERR_ARG, "bad device index");
+        ctx[i] = replica_on(s, devices[i], uses[devices[i]]++);
+        if (!ctx[i]) return RTC_ERR_CUDA;
+    }
+    PeerAccums A;
+    std::memset(&A, 0, sizeof A);
+    A.n = ndev;
+    rtc_scene* head = ctx[0];
+    // every device renders its sample range into its own buffer on its own stream
+    for (int i = 0; i < ndev; ++i) {
+        rtc_scene* c = ctx[i];
+        CU(cudaSetDevice(c->device));
+        if (!c->multi_stream) CU(cudaStreamCreateWithFlags(&c->multi_stream, cudaStreamNonBlocking));
+        if (!c->multi_done) CU(cudaEventCreateWithFlags(&c->multi_done, cudaEventDisableTiming));
+        CU(c->accum.ensure(nvalues));
+        CU(cudaMemsetAsync(c->accum.p, 0, nvalues * sizeof(float), c->multi_stream));
+        const uint32_t lo = (uint32_t)((uint64_t)i * samples / ndev), hi = (uint32_t)((uint64_t)(i + 1) * samples / ndev);
+        if ((rc = rtc_render_accumulate(c, seed, lo, hi - lo, c->accum.p, c->multi_stream))) return rc;
+        CU(cudaEventRecord(c->multi_done, c->multi_stream));
+        A.p[i] = c->accum.p;
+    }
+    // the head device reads the others' buffers in place (peer access), or copies them over when it cannot
+    CU(cudaSetDevice(head->device));
+    std::vector<float*> staged;
+    for (int i = 1; i < ndev; ++i) {
+        rtc_scene* c = ctx[i];
+        CU(cudaStreamWaitEvent(head->multi_stream, c->multi_done, 0));
+        if (c->device == head->device) continue;
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, head->device, c->device));
+        bool mapped = false;
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(c->device, 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); mapped = true; }
+            else cudaGetLastError();
+        }
+        if (!mapped) {
+            float* tmp = nullptr;
+            CU(cudaMalloc(&tmp, nvalues * sizeof(float)));
+            staged.push_back(tmp);
+            CU(cudaMemcpyPeerAsync(tmp, head->device, c->accum.p, c->device, nvalues * sizeof(float), head->multi_stream));
+            A.p[i] = tmp;
+        }
+    }
+    CU(head->rgb.ensure(nvalues));
+    float* sum_dev = nullptr;
+    if (sum_host) { CU(head->frames[1].accum.ensure(nvalues)); sum_dev = head->frames[1].accum.p; }
+    LaunchCtx lc{head->multi_stream, head->sms};
+    if (head->host.dialect == DIALECT_HW1) {
+        // hw1 writes colours as they are: only the device that holds sample 0 has any
+        launch_resolve_flat(lc, A.p[0], 1.f, (uint32_t)nvalues, head->rgb.p);
+        if (sum_dev) CU(cudaMemcpyAsync(sum_dev, A.p[0], nvalues * sizeof(float), cudaMemcpyDeviceToDevice, head->multi_stream));
+    } else launch_resolve_peers(lc, A, 1.f / (float)samples, (uint32_t)nvalues, head->rgb.p, sum_dev);
+    head->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rgb_host, head->rgb.p, nvalues, cudaMemcpyDeviceToHost, head->multi_stream));
+    if (sum_host) CU(cudaMemcpyAsync(sum_host, sum_dev, nvalues * sizeof(float), cudaMemcpyDeviceToHost, head->multi_stream));
+    CU(cudaStreamSynchronize(head->multi_stream));
+    for (float* t : staged) cudaFree(t);
+    CU(cudaSetDevice(s->device));
+    return RTC_OK;
+}
+int rtc_render_ppm_multi(rtc_scene* s, const int* devices, int ndev, uint32_t seed, const char* out_path) {
+    if (!s || !out_path) return fail(RTC_ERR_ARG, "null argument");
+    size_t nvalues = 3 * (size_t)s->host.cam.width * s->host.cam.height;
+    std::vector<uint8_t> img(nvalues);
+    int rc = rtc_render_u8_multi(s, devices, ndev, seed, img.data(), nullptr);
     if (rc) return rc;
     std::ofstream out(out_path, std::ios::binary);
     if (!out) return fail(RTC_ERR_IO, std::string("cannot open output file ") + out_path);

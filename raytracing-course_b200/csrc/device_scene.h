@@ -19,7 +19,7 @@ struct DevScene {
     const float4* xf_rot;  // quaternion xyzw
     const float4* mat0;    // (colour, bits(material))
     const float4* mat1;    // (emission, ior)
-    // index BVH: 8 float4 (128 B) per 4-wide node, child-major (scene_host.h kIndexNodeF4)
+    // index BVH: 6 float4 (96 B) per 4-wide node: fp16 child boxes, child refs, fp16 child direction cones
     const float4* inodes;
     // reference BVH: 2 float4 per node + meta
     const float4* rnodes;
@@ -52,8 +52,8 @@ inline void fill_dev_scalars(const HostScene& host, DevScene& S) {
     S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
     for (int c = 0; c < 4; ++c) S.iroot_ref[c] = IREF_NONE;
     if (host.flat.iroot != IREF_NONE && !(host.flat.iroot & IREF_LEAF)) {
-        for (int c = 0; c < 4; ++c)   // the last word of each child
-            memcpy(&S.iroot_ref[c], &host.flat.inodes[kIndexNodeF4 * (size_t)host.flat.iroot + kIndexChildF4 * c + 1].w, 4);
+        const f4& refs = host.flat.inodes[kIndexNodeF4 * (size_t)host.flat.iroot + 3];   // words 12..15 of the node
+        memcpy(S.iroot_ref, &refs, sizeof S.iroot_ref);
     }
     S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;
     S.width = host.cam.width; S.height = host.cam.height; S.ray_depth = host.ray_depth;

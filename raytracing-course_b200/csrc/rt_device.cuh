@@ -401,21 +401,44 @@ RT_D BestHit replay_reference(const DevScene& S, vec3 o, vec3 d, float cd0, Leaf
     return cur;
 }
 
-// One index-BVH node = 128 bytes = 4 children of 32 bytes each (scene_host.h kIndexNodeF4): centre in fp32, half-extents
-// in fp16 rounded UP, one direction cone (axis, threshold) in fp16, the child reference.  Conservative boxes only
-// ever ADD candidates: every leaf is re-tested against its EXACT float box before its primitives are (leaf_test).
+// One index-BVH node = 96 bytes: the boxes of its 4 children as fp16 rounded OUTWARD (64 bytes with the refs) + one
+// direction cone per child (32 bytes, cone_cull_pair below)
+// (min.x[4] min.y[4] min.z[4] max.x[4] | max.y[4] max.z[4] refs[4]), read with two 32-byte loads.
+// The traversal is bound by the L1 misses an SM can keep in flight (profiles/r01_experiments.md),
+// so node bytes are what counts; conservative boxes only add candidates, and every leaf is
+// re-tested against its EXACT float box before its primitives are (leaf_test).
+// Slab tests in min/max form with the reciprocal direction.  tc = box entry distance, or -inf when
+// the origin is inside (the reference's `interior`).
 // Reciprocal direction for the slab tests, clamped to +-1e30: a zero direction component would give
 // inf and then inf - inf = NaN in c * inv - o * inv, which the 3-input min/max drop, i.e. the axis would
 // not constrain at all and such a ray (about one in 10^7) would walk a whole slab of the tree and hold
-// a persistent launch for milliseconds.  With a finite reciprocal the test is simply exact.
+// a persistent k_traverse launch for milliseconds.  With a finite reciprocal the test is simply exact.
+#ifndef RTC_FAST_RAY_INV
+#define RTC_FAST_RAY_INV 1   // measured on B200: k_traverse 11.70 -> 11.56 ms, k_shade 7.14 -> 7.07 ms
+#endif
 RT_D vec3 ray_inv(vec3 d) {
     const float big = 1e30f;
+#if RTC_FAST_RAY_INV && defined(__CUDA_ARCH__)
+    // approximate reciprocal (MUFU.RCP, 1 ulp): the slab tests of the index nodes are conservative by more than that
+    // and leaf_box re-decides everything inside its 2e-6 band exactly
+    return mk3(fminf(fmaxf(__fdividef(1.0f, d.x), -big), big), fminf(fmaxf(__fdividef(1.0f, d.y), -big), big), fminf(fmaxf(__fdividef(1.0f, d.z), -big), big));
+#else
     return mk3(fminf(fmaxf(1.0f / d.x, -big), big), fminf(fmaxf(1.0f / d.y, -big), big), fminf(fmaxf(1.0f / d.z, -big), big));
+#endif
 }
 struct NodeVisit {
     uint32_t ref[kNodeWidth];
     bool hit[kNodeWidth];
 };
+RT_D void slab(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, vec3 inv, vec3 oi, uint32_t ref, bool& hit, float& tc) {
+    float x1 = fmaf(mnx, inv.x, -oi.x), x2 = fmaf(mxx, inv.x, -oi.x);
+    float y1 = fmaf(mny, inv.y, -oi.y), y2 = fmaf(mxy, inv.y, -oi.y);
+    float z1 = fmaf(mnz, inv.z, -oi.z), z2 = fmaf(mxz, inv.z, -oi.z);
+    float t1 = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    float t2 = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    hit = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
+    tc = t1 < 0.f ? -kInfF : t1;
+}
 // 32-byte read-only load (LDG.E.256 on sm_100a)
 RT_D void ldg8(const float4* p, float4& a, float4& b) {
 #ifdef __CUDA_ARCH__
@@ -431,6 +454,20 @@ RT_D float2 unpack_half2(float word) {
     uint32_t u = __float_as_uint(word);
     return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
+#if RTC_NODE_CENTRE_HALF
+// child box = centre +- half: entry/exit per axis are tc -+ h * |inv| with tc = c * inv - o * inv, three
+// FFMA and no min/max (the kernel is bound by the ALU pipe, which FMNMX shares with the integer
+// bookkeeping).  Against the exact leaf test (slab) the two roundings can move entry/exit by a few ulp of
+// t; fp16 rounding of c and h (outward) is three orders of magnitude larger except for boxes whose faces
+// are exactly representable in fp16, where a ray within ~1e-6 of grazing a face may be decided the other way.
+RT_D void slab_ch(float cx, float cy, float cz, float hx, float hy, float hz, vec3 inv, vec3 oi, uint32_t ref, bool& hit) {
+    float tx = fmaf(cx, inv.x, -oi.x), ty = fmaf(cy, inv.y, -oi.y), tz = fmaf(cz, inv.z, -oi.z);
+    float ax = fabsf(inv.x), ay = fabsf(inv.y), az = fabsf(inv.z);
+    float t1 = fmaxf(fmaxf(fmaf(-hx, ax, tx), fmaf(-hy, ay, ty)), fmaf(-hz, az, tz));
+    float t2 = fminf(fminf(fmaf(hx, ax, tx), fmaf(hy, ay, ty)), fmaf(hz, az, tz));
+    hit = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
+}
+#endif
 // Feasibility cones (bvh_build.cpp Cone): the normalised ray direction as halves, (x, y) and (z, z).
 struct ConeDir {
     uint32_t xy, zz;
@@ -449,54 +486,68 @@ RT_D ConeDir cone_dir(vec3 d) {
     c.zz = pack_half2(e.z * k, e.z * k);
     return c;  // a zero or non-finite direction gives NaN halves: every comparison below is then false = not culled
 }
-// A child cannot be hit by a ray of direction dn when |dn . axis| < threshold, evaluated in half arithmetic (the
-// thresholds carry the rounding slack, bvh_build.cpp emit): (ax dx, ay dy) -> (az dz + ax dx, ay dy) -> sum -> compare.
-// w_axy = axis.x | axis.y << 16, w_az = axis.z (high half 0), thr = the threshold's half bits; NaN compares false.
-RT_D bool cone_culls(ConeDir dn, uint32_t w_axy, uint32_t w_az, uint32_t thr) {
+// children (2j, 2j + 1) of a node: bit 0 / bit 16 set when the child cannot be hit by a ray of this direction,
+// |dn . axis| < threshold in half arithmetic (the thresholds carry the rounding slack, bvh_build.cpp emit)
+RT_D uint32_t cone_cull_pair(ConeDir dn, float wx, float wy, float wz, float wt) {
 #ifdef __CUDA_ARCH__
     const __half2 xy = *reinterpret_cast<const __half2*>(&dn.xy), zz = *reinterpret_cast<const __half2*>(&dn.zz);
-    const __half2 axy = *reinterpret_cast<const __half2*>(&w_axy), az0 = *reinterpret_cast<const __half2*>(&w_az);
-    const __half2 dt = __hfma2(az0, zz, __hmul2(axy, xy));
-    const __half sum = __hadd(__low2half(dt), __high2half(dt));
-    const unsigned short tb = (unsigned short)thr;
-    return __hlt(__habs(sum), *reinterpret_cast<const __half*>(&tb));
+    const uint32_t ux = __float_as_uint(wx), uy = __float_as_uint(wy), uz = __float_as_uint(wz), ut = __float_as_uint(wt);
+    const __half2 ax = *reinterpret_cast<const __half2*>(&ux), ay = *reinterpret_cast<const __half2*>(&uy);
+    const __half2 az = *reinterpret_cast<const __half2*>(&uz), th = *reinterpret_cast<const __half2*>(&ut);
+    __half2 dt = __hmul2(ax, __low2half2(xy));
+    dt = __hfma2(ay, __high2half2(xy), dt);
+    dt = __hfma2(az, zz, dt);
+    return __hlt2_mask(__habs2(dt), th) & 0x00010001u;
 #else
     // host compilation (tests/host_emul): the same operations, each rounded to half
     auto h = [](float f) { return __half2float(__float2half_rn(f)); };
     const float2 d_xy = unpack_half2(__uint_as_float(dn.xy)), d_zz = unpack_half2(__uint_as_float(dn.zz));
-    const float2 axy = unpack_half2(__uint_as_float(w_axy)), az0 = unpack_half2(__uint_as_float(w_az));
-    const float lo = h(fmaf(az0.x, d_zz.x, h(axy.x * d_xy.x))), hi = h(fmaf(az0.y, d_zz.y, h(axy.y * d_xy.y)));
-    const float sum = h(lo + hi);
-    const float t = unpack_half2(__uint_as_float(thr & 0xFFFFu)).x;
-    return fabsf(sum) < t;
+    const float2 ax = unpack_half2(wx), ay = unpack_half2(wy), az = unpack_half2(wz), th = unpack_half2(wt);
+    float d0 = h(ax.x * d_xy.x), d1 = h(ax.y * d_xy.x);
+    d0 = h(fmaf(ay.x, d_xy.y, d0)); d1 = h(fmaf(ay.y, d_xy.y, d1));
+    d0 = h(fmaf(az.x, d_zz.x, d0)); d1 = h(fmaf(az.y, d_zz.x, d1));
+    return (fabsf(d0) < th.x ? 1u : 0u) | (fabsf(d1) < th.y ? 0x10000u : 0u);
 #endif
 }
-// One child (its two float4) against one ray: child box = centre +- half, entry/exit per axis are tc -+ h |inv| with
-// tc = c * inv - o * inv (FFMA only), then the cone.  Against the exact leaf test the roundings can move entry / exit
-// by a few ulp of t; the builder's slack on the half-extents covers that.
-RT_D bool index_child_hit(float4 c0, float4 c1, vec3 inv, vec3 oi, ConeDir dn, uint32_t& ref) {
-    ref = __float_as_uint(c1.w);
-    const float2 hxy = unpack_half2(c0.w);
-    const uint32_t w_hz_thr = __float_as_uint(c1.x);
-    const float hz = unpack_half2(c1.x).x;
-    const float tx = fmaf(c0.x, inv.x, -oi.x), ty = fmaf(c0.y, inv.y, -oi.y), tz = fmaf(c0.z, inv.z, -oi.z);
-    const float ax = fabsf(inv.x), ay = fabsf(inv.y), az = fabsf(inv.z);
-    const float t1 = fmaxf(fmaxf(fmaf(-hxy.x, ax, tx), fmaf(-hxy.y, ay, ty)), fmaf(-hz, az, tz));
-    const float t2 = fminf(fminf(fmaf(hxy.x, ax, tx), fmaf(hxy.y, ay, ty)), fmaf(hz, az, tz));
-    const bool box = t1 <= t2 && t2 >= 0.f && ref != IREF_NONE;
-    return box && !cone_culls(dn, __float_as_uint(c1.y), __float_as_uint(c1.z), w_hz_thr >> 16);
+// one block of 4 children: boxes, refs, cones (ref / hit point at the block's 4 entries of the NodeVisit)
+RT_D void index_visit_block(const float4* nd, vec3 inv, vec3 oi, ConeDir dn, uint32_t* ref, bool* hit) {
+    float4 q0, q1, q2, q3;
+    ldg8(nd, q0, q1);
+    ldg8(nd + 2, q2, q3);
+    // q0 = min.x[0..3] min.y[0..3] ; q1 = min.z max.x ; q2 = max.y max.z ; q3 = refs
+    // (centre/half layout: centre in place of min, half-extent in place of max)
+    const float2 ax01 = unpack_half2(q0.x), ax23 = unpack_half2(q0.y), ay01 = unpack_half2(q0.z), ay23 = unpack_half2(q0.w);
+    const float2 az01 = unpack_half2(q1.x), az23 = unpack_half2(q1.y), bx01 = unpack_half2(q1.z), bx23 = unpack_half2(q1.w);
+    const float2 by01 = unpack_half2(q2.x), by23 = unpack_half2(q2.y), bz01 = unpack_half2(q2.z), bz23 = unpack_half2(q2.w);
+    ref[0] = __float_as_uint(q3.x); ref[1] = __float_as_uint(q3.y);
+    ref[2] = __float_as_uint(q3.z); ref[3] = __float_as_uint(q3.w);
+#if RTC_NODE_CENTRE_HALF
+    slab_ch(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, ref[0], hit[0]);
+    slab_ch(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, ref[1], hit[1]);
+    slab_ch(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, ref[2], hit[2]);
+    slab_ch(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, ref[3], hit[3]);
+#else
+    float tc;
+    slab(ax01.x, ay01.x, az01.x, bx01.x, by01.x, bz01.x, inv, oi, ref[0], hit[0], tc);
+    slab(ax01.y, ay01.y, az01.y, bx01.y, by01.y, bz01.y, inv, oi, ref[1], hit[1], tc);
+    slab(ax23.x, ay23.x, az23.x, bx23.x, by23.x, bz23.x, inv, oi, ref[2], hit[2], tc);
+    slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, ref[3], hit[3], tc);
+#endif
+#if RTC_NODE_CONES
+    float4 q4, q5;
+    ldg8(nd + 4, q4, q5);  // axis.x[0..3] axis.y[0..3] | axis.z[0..3] threshold[0..3]
+    const uint32_t c01 = cone_cull_pair(dn, q4.x, q4.z, q5.x, q5.z), c23 = cone_cull_pair(dn, q4.y, q4.w, q5.y, q5.w);
+    hit[0] = hit[0] && !(c01 & 1u); hit[1] = hit[1] && !(c01 >> 16);
+    hit[2] = hit[2] && !(c23 & 1u); hit[3] = hit[3] && !(c23 >> 16);
+#else
+    (void)dn;
+#endif
 }
-// all four children of a node for ONE ray (the root visit of pre_step, the straight-line traversal below; k_traverse_pool
-// gives every child of a node to a lane of its own)
 RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi, ConeDir dn) {
     const float4* nd = S.inodes + kIndexNodeF4 * (size_t)node;
     NodeVisit v;
 #pragma unroll
-    for (uint32_t c = 0; c < kNodeWidth; ++c) {
-        float4 c0, c1;
-        ldg8(nd + kIndexChildF4 * c, c0, c1);
-        v.hit[c] = index_child_hit(c0, c1, inv, oi, dn, v.ref[c]);
-    }
+    for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) index_visit_block(nd + kIndexBlockF4 * blk, inv, oi, dn, v.ref + 4 * blk, v.hit + 4 * blk);
     return v;
 }
 // closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)

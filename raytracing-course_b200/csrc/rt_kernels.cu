@@ -5,8 +5,8 @@
 //   pre_step    (fused into the kernel that creates the ray: k_generate, k_shade; k_pre for the probes) closest
 //               plane + the root of the index BVH; rays that touch no root child are finished, the others are
 //               queued (warp-aggregated atomics) together with the root children they enter, for
-//   k_traverse  persistent warps that keep a pool of rays, one stack of node tasks and a queue of leaf tasks in
-//               shared memory: all reference leaves a ray touches, then the replay of the reference recursion;
+//   k_traverse  persistent warps that pull rays from that queue; every lane refills itself as soon as its ray is
+//               done: all reference leaves a ray touches, then the replay of the reference recursion;
 //   k_shade     recomputes the hit of the winning primitive (normal, interior), applies the material, writes
 //               surviving paths compacted into the next queue.
 #include "rt_device.cuh"
@@ -14,6 +14,7 @@
 
 namespace rtc {
 
+static_assert(kNodeWidth == 4, "a traverse-queue entry carries the 4 root children a ray enters");
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = 32;           // queue slots a warp reserves per atomic
 
@@ -126,320 +127,179 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 }
 
 // ------------------------------------------------------------------------------- extend, step 2
-// BVH_t::Intersect (src/bvh.cpp:181-225) for the queued rays: index-BVH traversal collecting the reference leaves
-// with a hit, then the replay of the reference recursion (rt_device.cuh).
+// BVH_t::Intersect (src/bvh.cpp:181-225) for the queued rays: index-BVH traversal collecting the
+// reference leaves with a hit, then the replay of the reference recursion (rt_device.cuh).
 //
-// What bounds this stage is the L1 data pipe: every node fetch of every ray is a scattered access, and a load
-// instruction costs one wavefront per distinct line its lanes touch (ncu, round 2: l1tex__data_pipe_lsu_wavefronts at
-// 66 - 80 % of peak while issue slots idle; the first kernel of this name, where a lane owned a ray and read its 96-byte
-// node with three 32-byte loads, paid three wavefronts per node visit at 19 of 32 lanes busy).  So:
-//   * a node is ONE 128-byte line of four 32-byte children, fetched by a QUAD of lanes with one load each -- one
-//     wavefront per node -- and every lane tests the child it loaded;
-//   * the lanes of a warp are decoupled from its rays.  A warp keeps, in SHARED MEMORY, kPoolSlots resident rays
-//     (reciprocal direction, origin, cone direction, closest plane, pending-task count), ONE stack of node tasks
-//     (slot, node) for all of them and a queue of leaf tasks (slot, leaf).  A VISIT step pops the top 32 node tasks
-//     -- whichever rays they belong to, several of one ray if it has them -- and works through them eight at a time;
-//     hit children go back on the stack / the leaf queue at positions taken from warp ballots.  The all-hits traversal
-//     has no order, so any task order is correct, and a ray that needs hundreds of visits is worked on by many lanes
-//     at once instead of holding a launch behind one lane.  A LEAF step tests 32 queued leaves, whoever owns them.
-//     A ray is done when its pending count (stacked + queued tasks) reaches zero; a RETIRE step replays the reference
-//     recursion for up to 32 done rays and loads new rays into their slots.
-// Children are pushed in the stack order of their parents, so the tasks of one ray stay contiguous on the stack: among
-// the 32 popped tasks those of one ray are neighbours, and the last of them adds the ray's net task count to the slot
-// -- one writer per slot and step, no atomics.
-#ifndef RTC_POOL_SLOTS
-#define RTC_POOL_SLOTS 48
+// Persistent warps with a per-warp task scheduler.  The traversal reports ALL touched leaves in
+// any order, so the three kinds of work of a ray are decoupled: VISIT one inner node (children
+// that are leaves are only noted down), test one noted LEAF, FINISH the ray (replay + store);
+// idle lanes REFILL from the queue.  Every iteration the warp votes and executes the kind most
+// lanes are ready for, which keeps lanes busy although rays need between one and several
+// hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
+constexpr int kStackWords = 56;  // per lane: inner-node stack from the bottom, noted leaves from the top
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+#ifndef RTC_LEAF_FIRST
+#define RTC_LEAF_FIRST 8
 #endif
-#ifndef RTC_POOL_STACK
-#define RTC_POOL_STACK 320
+#ifndef RTC_VISIT_QUORUM
+#define RTC_VISIT_QUORUM 16   // sweep on B200 with cone nodes: 10: 20.2, 12: 19.7, 14: 19.3, 16: 19.05 ms/step (64-byte nodes: 14 was best)
 #endif
-#ifndef RTC_POOL_RETIRE_MIN
-#define RTC_POOL_RETIRE_MIN 16   // done rays that start a RETIRE step although node tasks are waiting
-#endif
-#ifndef RTC_POOL_MIN_BLOCKS
-#define RTC_POOL_MIN_BLOCKS 5
-#endif
-constexpr int kPoolSlots = RTC_POOL_SLOTS;
-constexpr int kPoolStack = RTC_POOL_STACK;
-constexpr int kPoolLeafCap = 32 + 32 * (int)kNodeWidth;  // a LEAF step runs at 32 queued leaves; a step adds at most W per task
-constexpr int kSlotF4 = 5;                               // 80-byte slots: consecutive slots start 20 banks apart
-constexpr int kSlotWords = 4 * kSlotF4;
-constexpr int kSlotRec = 16, kSlotPending = 17;          // word 16: leaf records (bit 31: overflow), word 17: pending tasks
-constexpr uint32_t kTaskNodeBits = 26;
-constexpr uint32_t kTaskNodeMask = (1u << kTaskNodeBits) - 1u;
-constexpr uint32_t kSlotOverflow = 0x80000000u;
-static_assert(kNodeWidth == 4, "a quad of lanes per node, 4 root children per traverse-queue entry");
-static_assert(kPoolSlots >= 32 && kPoolSlots <= 64, "6 bits of a task hold the slot");
-static_assert(kPoolStack >= 64 + 2 * 32 * (int)kNodeWidth, "room for a RETIRE step (W tasks per new ray) on top of a working stack");
+constexpr int kVisitQuorum = RTC_VISIT_QUORUM;
+#ifndef RTC_LAZY_OVERFLOW
+#define RTC_LAZY_OVERFLOW 1
+#endif  // at least this many lanes ready to visit: skip the full vote
 
-struct __align__(16) WarpPool {
-    float4 slot[kPoolSlots * kSlotF4];  // (inv.xyz oi.x) (oi.yz dn.xy dn.zz) (o.xyz d.x) (d.yz cd0 ray) (records pending - -)
-    uint32_t stack[kPoolStack];         // node tasks: slot << 26 | node
-    uint32_t leaf_ref[kPoolLeafCap];    // leaf tasks: the leaf reference ...
-    uint8_t leaf_slot[kPoolLeafCap];    // ... and the slot of its ray
-    uint8_t done[64];                   // slots whose ray is finished (or that never held one)
-};
-size_t traverse_pool_record_bytes(int sms) {
-    return (size_t)sms * 16 * 4 * kPoolSlots * kMaxRecords * sizeof(LeafRec);   // at most 16 blocks of 4 warps per SM
-}
-// inclusive prefix sum over the lanes of a warp
-RT_D uint32_t warp_scan(uint32_t v, uint32_t lane) {
-#pragma unroll
-    for (int ofs = 1; ofs < 32; ofs <<= 1) {
-        const uint32_t up = __shfl_up_sync(kFullMask, v, ofs);
-        if ((int)lane >= ofs) v += up;
-    }
-    return v;
-}
-
+#ifndef RTC_TRAVERSE_MIN_BLOCKS
+#define RTC_TRAVERSE_MIN_BLOCKS 7   // 72 registers; 5 / 6 / 8 blocks (84 / 79 / 64 registers): 12.96 / 11.73 / 12.75 ms against 11.56
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(128, RTC_POOL_MIN_BLOCKS) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
-                                                                        uint32_t* cursor, LeafRec* recpool, unsigned long long* stats) {
-    __shared__ WarpPool pools[4];
+__global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevScene S, PathSoA P, HitSoA H, const uint32_t* tq, const uint32_t* tq_count,
+                                                   uint32_t* cursor, unsigned long long* stats) {
     const uint32_t total = *tq_count;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t sub = lane & 3u, quad = lane >> 2;   // VISIT: child `sub` of the node of quad `quad`
-    WarpPool& W = pools[warp];
-    LeafRec* const myrec = recpool + ((size_t)blockIdx.x * 4 + warp) * kPoolSlots * kMaxRecords;
-    uint32_t* const slotw = reinterpret_cast<uint32_t*>(W.slot);   // word w of slot k at kSlotWords * k + w
-    // warp-uniform state
-    int height = 0, nleaf = 0, ndone = kPoolSlots;
-    uint32_t pool_base = 0, pool_left = 0;
-    bool exhausted = false;
+    uint32_t pool_base = 0, pool_left = 0;  // warp-uniform
+    bool exhausted = false;                 // warp-uniform: the queue has no more slots for this warp
+    bool active = false, overflow = false;
+    uint32_t ray = 0, node = kNone;
+    vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), inv = mk3(0, 0, 0), oi = mk3(0, 0, 0);
+    ConeDir dn{0u, 0u};
+    float cd0 = 0.f;
+    int sp = 0, nl = 0, k = 0;
+    uint32_t stk[kStackWords];
+    LeafRec rec[kMaxRecords];
     uint32_t visits = 0, tests = 0, fallbacks = 0;
-    uint32_t iters[4] = {0, 0, 0, 0}, busy[4] = {0, 0, 0, 0};
-    for (int k = (int)lane; k < kPoolSlots; k += 32) {   // every slot starts empty and "done"
-        W.done[k] = (uint8_t)k;
-        slotw[kSlotWords * k + kSlotRec] = 0u;
-        slotw[kSlotWords * k + kSlotPending] = 0u;
-    }
-    __syncwarp();
+    uint32_t iters[4] = {0, 0, 0, 0}, busy[4] = {0, 0, 0, 0};  // STATS: warp iterations and participating lanes per kind
 
-    enum { kVisit, kLeaf, kRetire, kQuit };
-    uint32_t guard = 0;
+    enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
-        // a scheduling bug must not hang the device: no launch comes near 2^22 steps per warp (reported as 10^6 fallbacks)
-        if (++guard > (1u << 22)) { fallbacks += 1000000u; break; }
-        // ---------------------------------------------------------------- what next (warp-uniform)
-        int kind;
-        const bool can_load = !exhausted && height + 32 * (int)kNodeWidth <= kPoolStack;
-        if (nleaf >= 32) kind = kLeaf;
-        else if (ndone >= RTC_POOL_RETIRE_MIN && can_load) kind = kRetire;
-        else if (height >= 32) kind = kVisit;
-        else if (ndone > 0 && can_load) kind = kRetire;
-        else if (height > 0) kind = kVisit;
-        else if (nleaf > 0) kind = kLeaf;
-        else kind = kQuit;
-        if (kind == kQuit) {
-            // nothing stacked, nothing queued, no rays left: the rays still in the done list only need their replay
-            if (ndone == 0) break;
-            kind = kRetire;
+        const bool room = sp + nl + (2 * (int)kNodeWidth - 1) <= kStackWords;  // a visit notes up to W leaves and pushes up to W - 1 nodes
+#if !RTC_LAZY_OVERFLOW
+        if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
+#endif
+        const bool canV = active && node != kNone && room;
+        const unsigned mV = __ballot_sync(kFullMask, canV);
+        const int nV = __popc(mV);
+        int kind = kVisit;
+        bool canL = false, canF = false, canR = false;
+        unsigned mR = 0;
+        int nR = 0;
+        if (nV < kVisitQuorum) {  // full vote only when visiting would leave too many lanes idle
+#if RTC_LAZY_OVERFLOW
+            // a lane whose stack is full of inner nodes (no noted leaf to free room) gives up and takes the
+            // reference walk in FINISH; checked here only: such a lane is not in mV, so the vote comes
+            if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
+#endif
+            canL = active && nl > 0;
+            canF = active && node == kNone && nl == 0;
+            canR = !active && (pool_left > 0 || !exhausted);
+            const unsigned mL = __ballot_sync(kFullMask, canL), mF = __ballot_sync(kFullMask, canF);
+            mR = __ballot_sync(kFullMask, canR);
+            if (!(mV | mL | mF | mR)) break;
+            const int nL = __popc(mL), nF = __popc(mF);
+            nR = __popc(mR);
+            // lanes holding noted leaves are served before the plain majority vote once there are enough
+            // of them (threshold swept on B200: profiles/r01_experiments.md)
+            if (nL >= RTC_LEAF_FIRST) kind = kLeaf;
+            else
+            if (nV >= nL && nV >= nF && nV >= nR) kind = kVisit;
+            else if (nL >= nF && nL >= nR) kind = kLeaf;
+            else if (nF >= nR) kind = kFinish;
+            else kind = kRefill;
         }
 
+        if (STATS) {  // warp-execution efficiency of the scheduler: lanes that take part in this iteration
+            const bool part = kind == kVisit ? canV : kind == kLeaf ? canL : kind == kFinish ? canF : canR;
+            const int n = __popc(__ballot_sync(kFullMask, part));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (kind == q) { iters[q] += 1; busy[q] += (uint32_t)n; }
+        }
         if (kind == kVisit) {
-            // ------------------------------------------------------------ VISIT: the top 32 node tasks
-            int n = min(height, 32);
-            const int room = kPoolStack - height;          // a task is popped and may push W
-            if (room < n * ((int)kNodeWidth - 1)) n = room / ((int)kNodeWidth - 1);
-            if (n == 0) {
-                // The stack is full of tasks that may each push more: give up on the resident rays -- they take the
-                // reference walk when they are retired.  (Never seen; kept so that the kernel cannot deadlock.)
-                for (int base = 0; base < kPoolSlots; base += 32) {
-                    const int k = base + (int)lane;
-                    const bool live = k < kPoolSlots && slotw[kSlotWords * (k < kPoolSlots ? k : 0) + kSlotPending] != 0u;
-                    const unsigned m = __ballot_sync(kFullMask, live);
-                    if (live) {
-                        slotw[kSlotWords * k + kSlotRec] = kSlotOverflow;
-                        slotw[kSlotWords * k + kSlotPending] = 0u;
-                        W.done[ndone + __popc(m & lt_mask)] = (uint8_t)k;
+            // ---- VISIT: one inner node per ready lane; leaf children are only noted
+            if (canV) {
+                if (STATS) ++visits;
+                NodeVisit v = index_visit(S, node, inv, oi, dn);
+                const int spm = sp > 0 ? sp - 1 : 0;
+                const uint32_t top = stk[spm];
+                uint32_t next = kNone;
+#pragma unroll
+                for (int c = 0; c < (int)kNodeWidth; ++c) {
+                    const bool leaf = (v.ref[c] & IREF_LEAF) != 0;
+                    if (v.hit[c] && leaf) {  // note the leaf, test it later
+                        ++nl;
+                        stk[kStackWords - nl] = v.ref[c];
                     }
-                    ndone += __popc(m);
+                    const bool inner = v.hit[c] && !leaf;
+                    if (inner && next != kNone) { stk[sp] = v.ref[c]; ++sp; }
+                    next = (inner && next == kNone) ? v.ref[c] : next;
                 }
-                height = 0; nleaf = 0;
-                __syncwarp();
-                continue;
+                const bool pop = next == kNone && sp > 0;
+                node = pop ? top : next;
+                sp = pop ? spm : sp;
             }
-            if (STATS) { iters[0] += 1; busy[0] += (uint32_t)n; visits += (lane == 0) ? (uint32_t)n : 0u; }
-            // lane t holds task t = stack[height - n + t]: task order = stack order, and children are pushed in task order
-            height -= n;
-            const uint32_t mytask = (int)lane < n ? W.stack[height + (int)lane] : 0xFFFFFFFFu;
-            __syncwarp();   // the popped part of the stack is overwritten by the pushes below
-            // the node of task 8 r + quad, child `sub`: all loads first, they are independent
-            float4 c0[4], c1[4];
-            uint32_t task[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                task[r] = __shfl_sync(kFullMask, mytask, 8 * r + (int)quad);
-                if (8 * r + (int)quad < n) ldg8(S.inodes + kIndexNodeF4 * (size_t)(task[r] & kTaskNodeMask) + kIndexChildF4 * sub, c0[r], c1[r]);
-            }
-            uint32_t grown[4];   // per round: ballot of the children that were pushed (node or leaf task)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                grown[r] = 0u;
-                if (8 * r >= n) continue;   // warp-uniform
-                const uint32_t k = task[r] >> kTaskNodeBits;
-                bool hit = false;
-                uint32_t ref = 0u;
-                if (8 * r + (int)quad < n) {
-                    const float4 q0 = W.slot[kSlotF4 * k + 0], q1 = W.slot[kSlotF4 * k + 1];
-                    ConeDir dn;
-                    dn.xy = __float_as_uint(q1.z); dn.zz = __float_as_uint(q1.w);
-                    hit = index_child_hit(c0[r], c1[r], mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), dn, ref);
-                }
-                const bool leaf = (ref & IREF_LEAF) != 0u;
-                const unsigned im = __ballot_sync(kFullMask, hit && !leaf), lm = __ballot_sync(kFullMask, hit && leaf);
-                if (hit) {
-                    if (leaf) {
-                        const int q = nleaf + __popc(lm & lt_mask);
-                        W.leaf_ref[q] = ref; W.leaf_slot[q] = (uint8_t)k;
-                    } else W.stack[height + __popc(im & lt_mask)] = (k << kTaskNodeBits) | ref;
-                }
-                height += __popc(im);
-                nleaf += __popc(lm);
-                grown[r] = im | lm;
-            }
-            // pending counts, task-major again (lane t = task t): children of the tasks of one ray minus those tasks
-            const uint32_t k = mytask >> kTaskNodeBits;   // 63 for the lanes without a task
-            const uint32_t g = lane < 8 ? grown[0] : lane < 16 ? grown[1] : lane < 24 ? grown[2] : grown[3];
-            const uint32_t before = lane < 8 ? 0u : lane < 16 ? (uint32_t)__popc(grown[0])
-                                  : lane < 24 ? (uint32_t)(__popc(grown[0]) + __popc(grown[1]))
-                                  : (uint32_t)(__popc(grown[0]) + __popc(grown[1]) + __popc(grown[2]));
-            const uint32_t shift = 4u * (lane & 7u);
-            const uint32_t excl = before + (uint32_t)__popc(g & ((1u << shift) - 1u));          // children of the tasks before mine
-            const uint32_t incl = excl + (uint32_t)__popc((g >> shift) & 15u);
-            const bool act = (int)lane < n;
-            const uint32_t k_next = __shfl_down_sync(kFullMask, k, 1), k_prev = __shfl_up_sync(kFullMask, k, 1);
-            const bool first = act && (lane == 0 || k_prev != k);
-            const bool last = act && ((int)lane == n - 1 || k_next != k);
-            const unsigned firsts = __ballot_sync(kFullMask, first);
-            const int run_start = 31 - __clz(firsts & (lt_mask | (1u << lane)));      // first lane of my run
-            const uint32_t excl_start = __shfl_sync(kFullMask, excl, run_start < 0 ? 0 : run_start);
-            bool finished = false;
-            if (last) {
-                const int net = (int)(incl - excl_start) - ((int)lane - run_start + 1);
-                const int pending = (int)slotw[kSlotWords * k + kSlotPending] + net;
-                slotw[kSlotWords * k + kSlotPending] = (uint32_t)pending;
-                finished = pending == 0;
-            }
-            const unsigned fin = __ballot_sync(kFullMask, finished);
-            if (finished) W.done[ndone + __popc(fin & lt_mask)] = (uint8_t)k;
-            ndone += __popc(fin);
-            __syncwarp();
         } else if (kind == kLeaf) {
-            // ------------------------------------------------------------ LEAF: 32 queued reference leaves
-            const int n = min(nleaf, 32);
-            if (STATS) { iters[1] += 1; busy[1] += (uint32_t)n; }
-            bool finished = false;
-            int k = 0;
-            nleaf -= n;
-            if ((int)lane < n) {
-                const int at = nleaf + (int)lane;
-                const uint32_t ref = W.leaf_ref[at];
-                k = W.leaf_slot[at];
-                const float4 q0 = W.slot[kSlotF4 * k + 0], q1 = W.slot[kSlotF4 * k + 1];
-                const float4 q2 = W.slot[kSlotF4 * k + 2], q3 = W.slot[kSlotF4 * k + 3];
-                const vec3 inv = mk3(q0.x, q0.y, q0.z), oi = mk3(q0.w, q1.x, q1.y);
-                const vec3 o = mk3(q2.x, q2.y, q2.z), d = mk3(q2.w, q3.x, q3.y);
+            // ---- LEAF: one noted reference leaf per ready lane
+            if (canL) {
+                const uint32_t ref = stk[kStackWords - nl];
+                --nl;
                 float bt, tc; int bid;
                 if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, STATS ? &tests : nullptr) && bid >= 0) {
-                    const uint32_t at_rec = atomicAdd(&slotw[kSlotWords * k + kSlotRec], 1u) & ~kSlotOverflow;   // rare
-                    if (at_rec < (uint32_t)kMaxRecords) {
-                        LeafRec r;
-                        r.key = ref & 0xFFFFFFu; r.id = bid; r.t = bt; r.tcull = tc;
-                        myrec[k * kMaxRecords + at_rec] = r;
-                    } else atomicOr(&slotw[kSlotWords * k + kSlotRec], kSlotOverflow);
+                    if (k == kMaxRecords) { overflow = true; node = kNone; sp = 0; nl = 0; }
+                    else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc; ++k; }
                 }
-                // leaves of one ray are not neighbours in the queue: several lanes may settle the same slot
-                finished = atomicSub(&slotw[kSlotWords * k + kSlotPending], 1u) == 1u;
             }
-            const unsigned fin = __ballot_sync(kFullMask, finished);
-            if (finished) W.done[ndone + __popc(fin & lt_mask)] = (uint8_t)k;
-            ndone += __popc(fin);
-            __syncwarp();
+        } else if (kind == kFinish) {
+            // ---- FINISH: replay of the reference recursion, store the winner
+            if (canF) {
+                BestHit b;
+                if (overflow) { b = trace_reftree(S, o, d, cd0); ++fallbacks; }
+                else b = replay_reference(S, o, d, cd0, rec, k);
+                if (b.id != -1 && b.t < cd0) WF_ST(H.id + ray, (uint32_t)b.id);  // src/scene.cpp:68-74
+                active = false;
+            }
         } else {
-            // ------------------------------------------------------------ RETIRE: replay + store, then a new ray
-            const int n = min(ndone, 32);
-            if (pool_left == 0 && !exhausted) {
+            // ---- REFILL idle lanes from the queue
+            if (pool_left == 0) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(cursor, kChunk);
                 base = __shfl_sync(kFullMask, base, 0);
                 if (base >= total) exhausted = true;
                 else { pool_base = base; pool_left = min(kChunk, total - base); }
             }
-            const bool can_push = height + 32 * (int)kNodeWidth <= kPoolStack;
-            const int serve = (exhausted || !can_push) ? 0 : min(n, (int)pool_left);
-            if (STATS) { iters[2] += 1; busy[2] += (uint32_t)n; if (serve) { iters[3] += 1; busy[3] += (uint32_t)serve; } }
-            ndone -= n;
-            const bool act = (int)lane < n;
-            const int k = act ? (int)W.done[ndone + (int)lane] : 0;
-            __syncwarp();   // the list is appended to again below
-            if (act) {
-                const uint32_t cnt = slotw[kSlotWords * k + kSlotRec];
-                if (cnt != 0) {   // rays without a hit leaf (most) have nothing to store: H.id holds the plane
-                    const float4 q2 = W.slot[kSlotF4 * k + 2], q3 = W.slot[kSlotF4 * k + 3];
-                    const vec3 o = mk3(q2.x, q2.y, q2.z), d = mk3(q2.w, q3.x, q3.y);
-                    const float cd0 = q3.z;
-                    const uint32_t ray = __float_as_uint(q3.w);
-                    BestHit b;
-                    if (cnt & kSlotOverflow) { b = trace_reftree(S, o, d, cd0); ++fallbacks; }
-                    else {
-                        LeafRec rec[kMaxRecords];
-                        const int nr = (int)cnt;
-                        for (int i = 0; i < nr; ++i) rec[i] = myrec[k * kMaxRecords + i];
-                        b = replay_reference(S, o, d, cd0, rec, nr);
-                    }
-                    if (b.id != -1 && b.t < cd0) WF_ST(H.id + ray, (uint32_t)b.id);  // src/scene.cpp:68-74
-                    slotw[kSlotWords * k + kSlotRec] = 0u;
-                }
-            }
-            // lanes [0, serve) load a new ray into their slot, the others hand their (now empty) slot back
-            const bool take = (int)lane < serve;
-            uint32_t ci = 0, cl = 0, entry = 0;
-            if (take) {
-                entry = WF_LD(tq + pool_base + lane);
-                const uint32_t ray = entry & kTqSlotMask;
-                const float4 o4 = WF_LD(P.o + ray), d4 = WF_LD(P.d + ray);
-                const vec3 o = ld3(o4), d = ld3(d4);
-                const vec3 inv = ray_inv(d), oi = o * inv;
-                const ConeDir dn = cone_dir(d);
-                W.slot[kSlotF4 * k + 0] = make_float4(inv.x, inv.y, inv.z, oi.x);
-                W.slot[kSlotF4 * k + 1] = make_float4(oi.y, oi.z, __uint_as_float(dn.xy), __uint_as_float(dn.zz));
-                W.slot[kSlotF4 * k + 2] = make_float4(o.x, o.y, o.z, d.x);
-                W.slot[kSlotF4 * k + 3] = make_float4(d.y, d.z, d4.w, __uint_as_float(ray));
-                if (S.iroot & IREF_LEAF) cl = 1;
-                else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if ((entry >> (kTqSlotBits + c)) & 1u) { if (S.iroot_ref[c] & IREF_LEAF) ++cl; else ++ci; }
-                }
-                slotw[kSlotWords * k + kSlotPending] = ci + cl;
-            }
-            const uint32_t mine = ci | (cl << 16);
-            const uint32_t incl = warp_scan(mine, lane);
-            const uint32_t sum = __shfl_sync(kFullMask, incl, 31);
-            const uint32_t excl = incl - mine;
-            if (take) {
-                int p = height + (int)(excl & 0xFFFFu), q = nleaf + (int)(excl >> 16);
-                if (S.iroot & IREF_LEAF) { W.leaf_ref[q] = S.iroot; W.leaf_slot[q] = (uint8_t)k; }
-                else {
+            uint32_t rank = __popc(mR & lt_mask);
+            uint32_t serve = min((uint32_t)nR, pool_left);
+            if (canR && rank < serve) {
+                const uint32_t entry = WF_LD(tq + pool_base + rank);
+                ray = entry & kTqSlotMask;
+                o = ld3(WF_LD(P.o + ray));
+                const float4 d4 = WF_LD(P.d + ray);
+                d = ld3(d4);
+                cd0 = d4.w;
+                inv = ray_inv(d);
+                oi = o * inv;
+                dn = cone_dir(d);
+                sp = 0; nl = 0; k = 0; overflow = false;
+                active = true;
+                node = kNone;
+                if (S.iroot & IREF_LEAF) {  // single-leaf tree
+                    nl = 1;
+                    stk[kStackWords - 1] = S.iroot;
+                } else {
+                    // the root was visited when the ray was made (pre_step): start from the children it entered.
+                    // (Measured on B200: 6.56 instead of 7.56 visits per ray and the same 11.65 ms -- the root visit of
+                    // freshly loaded lanes shares its warp iteration and its cache line with everybody else's.)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        if (!((entry >> (kTqSlotBits + c)) & 1u)) continue;
                         const uint32_t ref = S.iroot_ref[c];
-                        if (ref & IREF_LEAF) { W.leaf_ref[q] = ref; W.leaf_slot[q] = (uint8_t)k; ++q; }
-                        else { W.stack[p] = ((uint32_t)k << kTaskNodeBits) | ref; ++p; }
+                        if (!((entry >> (kTqSlotBits + c)) & 1u)) continue;
+                        if (ref & IREF_LEAF) { ++nl; stk[kStackWords - nl] = ref; }
+                        else if (node == kNone) node = ref;
+                        else { stk[sp] = ref; ++sp; }
                     }
                 }
-            } else if (act && !exhausted) {
-                W.done[ndone + ((int)lane - serve)] = (uint8_t)k;   // replayed, empty: waits for the next RETIRE
             }
-            if (!exhausted) ndone += n - serve;
-            height += (int)(sum & 0xFFFFu);
-            nleaf += (int)(sum >> 16);
-            pool_base += (uint32_t)serve;
-            pool_left -= (uint32_t)serve;
-            __syncwarp();
+            pool_base += serve;
+            pool_left -= serve;
         }
     }
     if (fallbacks) atomicAdd(stats + 5, (unsigned long long)fallbacks);
@@ -650,6 +510,17 @@ __global__ void __launch_bounds__(256) k_resolve(const float* accum, float inv_s
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvalues; i += gridDim.x * blockDim.x)
         out[i] = to_u8(aces(__fmul_rn(inv_samples, accum[i])));
 }
+// Multi-device Scene::Render, last step on the first device: the per-device pixel sums (each device rendered its share
+// of the samples) are read where they lie -- peer pointers over NVLink -- summed in device order, and resolved to
+// 8 bits in the same pass (src/scene.cpp:201, 227-228, 247); `sum` (optional) keeps the float total.
+__global__ void __launch_bounds__(256) k_resolve_peers(PeerAccums A, float inv_samples, uint32_t nvalues, uint8_t* out, float* sum) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvalues; i += gridDim.x * blockDim.x) {
+        float v = A.p[0][i];
+        for (int r = 1; r < A.n; ++r) v += A.p[r][i];
+        if (sum) sum[i] = v;
+        out[i] = to_u8(aces(__fmul_rn(inv_samples, v)));
+    }
+}
 __global__ void __launch_bounds__(256) k_tonemap(const float* rgb, uint32_t nvalues, uint8_t* out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvalues; i += gridDim.x * blockDim.x)
         out[i] = to_u8(aces(rgb[i]));
@@ -742,12 +613,12 @@ static int resident_blocks(K kernel, int slot) {
     return cache[slot][dev];
 }
 void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t max_count, const uint32_t* tq,
-                     const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats, void* recpool) {
+                     const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats) {
     // persistent: exactly one resident wave of 128-thread blocks
     const int per_sm = count_visits ? resident_blocks(k_traverse<true>, 1) : resident_blocks(k_traverse<false>, 0);
-    int grid = grid_for((uint64_t)max_count, 128, c.sms, per_sm < 16 ? per_sm : 16);
-    if (count_visits) k_traverse<true><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, (LeafRec*)recpool, stats);
-    else k_traverse<false><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, (LeafRec*)recpool, stats);
+    int grid = grid_for((uint64_t)max_count, 128, c.sms, per_sm);
+    if (count_visits) k_traverse<true><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, stats);
+    else k_traverse<false><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, stats);
 }
 void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count) {
     k_extend_reftree<<<grid_for(max_count, 128, c.sms, 16), 128, 0, c.stream>>>(S, P, H, qcount);
@@ -777,6 +648,9 @@ void launch_fold(const LaunchCtx& c, const float4* accum4, float* accum, uint32_
 }
 void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out) {
     k_resolve<<<grid_for(nvalues, 256, c.sms, 8), 256, 0, c.stream>>>(accum, inv_samples, nvalues, out);
+}
+void launch_resolve_peers(const LaunchCtx& c, const PeerAccums& A, float inv_samples, uint32_t nvalues, uint8_t* out, float* sum) {
+    k_resolve_peers<<<grid_for(nvalues, 256, c.sms, 8), 256, 0, c.stream>>>(A, inv_samples, nvalues, out, sum);
 }
 void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out) {
     k_tonemap<<<grid_for(nvalues, 256, c.sms, 8), 256, 0, c.stream>>>(rgb, nvalues, out);

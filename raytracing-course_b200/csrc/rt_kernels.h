@@ -19,11 +19,8 @@ void launch_generate(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H,
 // (index BVH), or launch_extend_reftree alone (the reference-tree twin).
 void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count,
                 uint32_t* tq, uint32_t* tq_count);
-// recpool: traverse_pool_record_bytes(sms) bytes of scratch in HBM (leaf-hit records of the resident rays), owned by
-// the caller, one per concurrently running launch
-size_t traverse_pool_record_bytes(int sms);
 void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t max_count, const uint32_t* tq,
-                     const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats, void* recpool);
+                     const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats);
 void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count);
 // shading of queue P with hits H; survivors go to queue N with their pre_step results in HN / tq
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
@@ -34,6 +31,14 @@ void launch_fold(const LaunchCtx& c, const float4* accum4, float* accum, uint32_
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats);
 void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out);
 void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out);
+// per-device accumulation buffers of one multi-device frame (device pointers valid on the device that launches:
+// its own memory or peer-mapped memory), summed in order and resolved to 8 bits
+constexpr int kMaxPeers = 16;
+struct PeerAccums {
+    const float* p[kMaxPeers];
+    int n;
+};
+void launch_resolve_peers(const LaunchCtx& c, const PeerAccums& A, float inv_samples, uint32_t nvalues, uint8_t* out, float* sum);
 void launch_pack_rays(const LaunchCtx& c, long n, const float* o, const float* d, PathSoA P, uint32_t* q);
 void launch_unpack_hits(const LaunchCtx& c, const DevScene& S, long n, PathSoA P, HitSoA H, int32_t* id, float* t, float* nrm,
                         int32_t* interior);

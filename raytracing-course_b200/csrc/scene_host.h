@@ -7,6 +7,18 @@
 
 #include "vecmath.h"
 
+// Index-BVH child boxes as fp16 (centre, half-extent) instead of (min, max): the slab test then
+// runs on the FMA pipe (3 FFMA per child and axis) instead of 2 FFMA + 2 FMNMX; k_traverse is bound
+// by the ALU pipe (profiles/r01_experiments.md).  0 selects the min/max layout for A/B runs.
+// Index nodes carry a direction cone per child (DESIGN.md "Feasibility cones"): 6 float4 = 96 bytes per node
+// instead of 4 float4 = 64 bytes.  RTC_NODE_CONES=0 builds the plain 64-byte nodes.
+#ifndef RTC_NODE_CONES
+#define RTC_NODE_CONES 1
+#endif
+#ifndef RTC_NODE_CENTRE_HALF
+#define RTC_NODE_CENTRE_HALF 1
+#endif
+
 namespace rtc {
 
 // The course's five homework snapshots of the renderer read five dialects of the scene format and
@@ -85,7 +97,8 @@ struct FlatScene {
     std::vector<f4> xf_pos;            // (pos.xyz, bits(type|flags))
     std::vector<f4> xf_rot;            // quaternion xyzw
     std::vector<f4> mat0, mat1;        // (col.rgb, bits(material)) (emission.rgb, ior)
-    // index BVH, 4-wide, kIndexNodeF4 x f4 per node (128 bytes, child-major: see kIndexNodeF4); exact leaf boxes: ubox
+    // index BVH, 4-wide, kIndexNodeF4 x f4 per node (96 bytes): child boxes as fp16 rounded OUTWARD, refs, child cones
+    // (min.x[4] min.y[4] min.z[4] max.x[4] | max.y[4] max.z[4] refs[4]); exact leaf boxes: ubox
     std::vector<f4> inodes;
     uint32_t iroot = 0;  // child reference of the root (may be a leaf reference)
     // reference BVH: 2 x f4 per node (centre.xyz, bits(left)) (half.xyz, bits(right)) + meta
@@ -129,16 +142,16 @@ constexpr uint32_t IREF_NONE = 0xFFFFFFFFu;
 constexpr uint32_t IREF_FAST = 0x40000000u;     // leaf = one triangle with pos 0 and identity rotation
 constexpr uint32_t IREF_MAX_LEAF_PRIMS = 64;   // 6 bits (24..29)
 constexpr uint32_t IREF_MAX_PRIMS = 1u << 24;
-// An index node has 4 children and is ONE 128-byte line: child c occupies bytes [32 c, 32 c + 32) =
-//   centre.x centre.y centre.z (fp32) | half.x half.y (fp16) | half.z cone-threshold (fp16) | axis.x axis.y (fp16) |
-//   axis.z 0 (fp16) | child reference
-// so that the four lanes of a quad fetch one node with one 32-byte load each (one L1 wavefront per node: the
-// traversal is bound by the L1 data-pipe wavefronts of its scattered node fetches, profiles/r02_experiments.md).
-// Half-extents are rounded UP and carry the builder's slack; the cone of a child (DESIGN.md "Feasibility cones")
-// is its axis and threshold, threshold 0 = unrestricted.
-constexpr uint32_t kNodeWidth = 4;
-constexpr uint32_t kIndexChildF4 = 2;                          // float4 per child
-constexpr uint32_t kIndexNodeF4 = kIndexChildF4 * kNodeWidth;   // float4 per index node (128 bytes)
+// Children per index node: 4, or 8 = two 4-child blocks of the same layout fetched by ONE visit (the collapse
+// predicts 35 % fewer entered nodes at 8: profiles/r01_experiments.md; prepared for an A/B run, 4 is the measured
+// default).
+#ifndef RTC_NODE_WIDTH
+#define RTC_NODE_WIDTH 4
+#endif
+static_assert(RTC_NODE_WIDTH == 4 || RTC_NODE_WIDTH == 8, "index nodes hold 4 or 8 children");
+constexpr uint32_t kNodeWidth = RTC_NODE_WIDTH;
+constexpr uint32_t kIndexBlockF4 = RTC_NODE_CONES ? 6 : 4;                  // float4 per block of 4 children
+constexpr uint32_t kIndexNodeF4 = kIndexBlockF4 * (kNodeWidth / 4);          // float4 per index node
 
 Aabb aabb_of_primitive(const Primitive& p);  // AABB_t::AABB_t(const Primitive&) src/bvh.cpp:41-87
 

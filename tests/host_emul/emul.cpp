@@ -176,8 +176,8 @@ int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t*
     for (size_t i = nn; i-- > 0;) {
         int hh = 0;
         for (int c = 0; c < (int)kNodeWidth; ++c) {
-            uint32_t r;
-            memcpy(&r, &F.inodes[kIndexNodeF4 * i + kIndexChildF4 * c + 1].w, 4);   // the last word of a child
+            const uint32_t* w = (const uint32_t*)&F.inodes[kIndexNodeF4 * i + kIndexBlockF4 * (c / 4)];
+            uint32_t r = w[12 + (c & 3)];
             if (r == IREF_NONE || (r & IREF_LEAF)) continue;
             hh = std::max(hh, height[r] + 1);
         }
@@ -227,20 +227,24 @@ int emu_index_check(void* h, uint64_t* out /* [7] */) {
         st.pop_back();
         out[6] = std::max<uint64_t>(out[6], (uint64_t)it.depth);
         int used = 0;
-        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)it.node;
-        for (int c = 0; c < (int)kNodeWidth; ++c) {
-            const float4 c0 = nd[kIndexChildF4 * c], c1 = nd[kIndexChildF4 * c + 1];   // as index_child_hit decodes them
-            const uint32_t ref = __float_as_uint(c1.w);
-            if (ref == IREF_NONE) continue;
+        for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) {
+        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)it.node + kIndexBlockF4 * blk;
+        const float4 q0 = nd[0], q1 = nd[1], q2 = nd[2], q3 = nd[3];
+        float2 cx[2] = {unpack_half2(q0.x), unpack_half2(q0.y)}, cy[2] = {unpack_half2(q0.z), unpack_half2(q0.w)};
+        float2 cz[2] = {unpack_half2(q1.x), unpack_half2(q1.y)}, hx[2] = {unpack_half2(q1.z), unpack_half2(q1.w)};
+        float2 hy[2] = {unpack_half2(q2.x), unpack_half2(q2.y)}, hz[2] = {unpack_half2(q2.z), unpack_half2(q2.w)};
+        uint32_t refs[4] = {__float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z), __float_as_uint(q3.w)};
+        for (int c = 0; c < 4; ++c) {
+            if (refs[c] == IREF_NONE) continue;
             ++used;
-            const float2 hxy = unpack_half2(c0.w);
-            const float C[3] = {c0.x, c0.y, c0.z}, H[3] = {hxy.x, hxy.y, unpack_half2(c1.x).x};
+            auto pick = [&](float2* a) { return (c & 1) ? a[c >> 1].y : a[c >> 1].x; };
+            float C[3] = {pick(cx), pick(cy), pick(cz)}, H[3] = {pick(hx), pick(hy), pick(hz)};
             Item ch{0, it.depth + 1, {C[0] - H[0], C[1] - H[1], C[2] - H[2]}, {C[0] + H[0], C[1] + H[1], C[2] + H[2]}, true};
             if (it.bounded)  // a child also lies inside everything above it
                 for (int a = 0; a < 3; ++a) { ch.mn[a] = std::max(ch.mn[a], it.mn[a]); ch.mx[a] = std::min(ch.mx[a], it.mx[a]); }
-            if (ref & IREF_LEAF) {
+            if (refs[c] & IREF_LEAF) {
                 ++out[1];
-                uint32_t first = ref & 0xFFFFFFu;
+                uint32_t first = refs[c] & 0xFFFFFFu;
                 if (first >= seen.size()) { ++out[3]; continue; }
                 if (seen[first]) ++out[2];
                 seen[first] = 1;
@@ -249,9 +253,10 @@ int emu_index_check(void* h, uint64_t* out /* [7] */) {
                 for (int a = 0; a < 3; ++a)
                     if (!(ch.mn[a] <= emn[a] && emx[a] <= ch.mx[a])) { ++out[5]; break; }
             } else {
-                ch.node = ref;
+                ch.node = refs[c];
                 st.push_back(ch);
             }
+        }
         }
         if (used < 2 && it.node != S.iroot) ++out[4];
     }

@@ -375,3 +375,87 @@ def test_rays_aimed_at_the_rendered_triangles(rtc, gpu_scenes, oracle_scenes, na
     want = a.intersect(o[:k], d[:k])
     assert (fast[0][:k] == want[0]).mean() >= 0.9999, (fast[0][:k] != want[0]).sum()
     check_hits(tuple(x[:k] for x in fast), want, id_agree=0.9999)
+
+
+# ------------------------------------------------------------------------------- round 2: frames, devices, probes at rate
+def _devices_for_test(rtc):
+    """Two devices when the box has them, else the same device twice (two replicas, the whole multi-device path
+    -- sample split, per-replica render, reduce + resolve kernel -- on one GPU)."""
+    return [0, 1] if rtc.device_count() >= 2 else [0, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h,spp", [("lights_mix", 96, 64, 16), ("practice5_dragon_10k", 128, 128, 8)])
+def test_multi_device_render_equals_single_device(rtc, name, w, h, spp):
+    """Scene::Render over N devices of one process (rtc_render_u8_multi): the Philox streams depend on
+    (pixel, sample) only, so N sample shards summed over peer access are the 1-device frame up to float summation
+    order -- float sums within 1e-4 relative, 8-bit image within 1 LSB."""
+    s = rtc.Scene(path=scene_path(name), device=0)
+    s.override(w, h, spp)
+    one = s.RenderSum(seed=11, sample_count=spp)
+    img1 = s.Render(seed=11)
+    for devices in (_devices_for_test(rtc), [0, 0, 0]):
+        img, total = s.RenderMulti(devices, seed=11, want_sum=True)
+        ok = np.isfinite(one) & np.isfinite(total)
+        assert ok.mean() > 0.999
+        assert np.allclose(total[ok], one[ok], rtol=1e-4, atol=1e-5), np.abs(total[ok] - one[ok]).max()
+        assert (np.abs(img.astype(int) - img1.astype(int)) <= 1).mean() > 0.999
+    s.close()
+
+
+@pytest.mark.gpu
+def test_multi_device_cli(rtc, tmp_path):
+    """RTC_DEVICES=<list> ./run.sh <scene> <out.ppm>"""
+    from conftest import ROOT
+    devs = ",".join(str(d) for d in _devices_for_test(rtc))
+    outs = []
+    for extra in ({}, {"RTC_DEVICES": devs}):
+        out = tmp_path / ("cli_%d.ppm" % len(outs))
+        env = dict(os.environ, RTC_SAMPLES="8", RTC_WIDTH="96", RTC_HEIGHT="64", RTC_SEED="5", **extra)
+        r = subprocess.run([os.path.join(ROOT, "run.sh"), scene_path("practice5_2"), str(out)], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(np.frombuffer(out.read_bytes()[len(b"P6\n96 64\n255\n"):], np.uint8))
+    assert (np.abs(outs[0].astype(int) - outs[1].astype(int)) <= 1).mean() > 0.999
+
+
+@pytest.mark.gpu
+def test_frames_in_flight_equal_render(rtc):
+    """rtc_frame_begin / rtc_frame_end (async scene upload into the idle arena, render, resolve, image to pinned host
+    memory) with two frames queued: every frame is the image rtc_render_u8 gives for its seed."""
+    s = rtc.Scene(path=scene_path("practice5_dragon_10k"), device=0)
+    s.override(160, 120, 4)
+    want = [s.Render(seed=20 + i) for i in range(4)]
+    got = [np.zeros_like(want[0]) for _ in range(4)]
+    h2d = s.frame_begin(seed=20, slot=0)
+    assert h2d > 1000000
+    for i in range(1, 4):
+        s.frame_begin(seed=20 + i, slot=i & 1)
+        s.frame_end((i - 1) & 1, got[i - 1])
+    s.frame_end(1, got[3])
+    for a, b in zip(want, got):
+        assert (np.abs(a.astype(int) - b.astype(int)) <= 1).mean() > 0.999
+    with pytest.raises(rtc.RtcError):
+        s.frame_end(0)          # nothing in flight
+    s.close()
+
+
+@pytest.mark.gpu
+def test_intersect_on_device_arrays(rtc, gpu_scenes):
+    """rtc_intersect_dev (rays and results stay in HBM, pooled scratch, no allocation per call) == rtc_intersect."""
+    import torch
+    s = gpu_scenes("practice5_dragon_10k")
+    rng = np.random.default_rng(5)
+    n = 200000
+    o = rng.uniform(-4, 4, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    pid, t, nrm, inter = s.RayIntersection(o, d)
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    tid = torch.empty(n, dtype=torch.int32, device="cuda"); tt = torch.empty(n, dtype=torch.float32, device="cuda")
+    tn = torch.empty((n, 3), dtype=torch.float32, device="cuda"); ti = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(2):   # the second call reuses every scratch buffer
+        s.intersect_dev(n, to.data_ptr(), td.data_ptr(), tid.data_ptr(), tt.data_ptr(), tn.data_ptr(), ti.data_ptr(),
+                        stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(tid.cpu().numpy(), pid)
+    assert np.array_equal(tt.cpu().numpy(), t)
+    assert np.array_equal(ti.cpu().numpy(), inter)

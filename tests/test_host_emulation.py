@@ -296,7 +296,7 @@ def test_index_tree_is_pinned(emu):
     measurement (profiles/)."""
     emu.emu_index_hash.restype = C.c_uint64
     emu.emu_index_hash.argtypes = [C.c_void_p]
-    want = {"practice5_dragon_10k": 0x11331ba32548ab00, "practice5_dragon_100k": 0xe9d3082fd1831cd7}
+    want = {"practice5_dragon_10k": 0x3489f252dd17952d, "practice5_dragon_100k": 0x8db8c0679a8cf812}
     if os.environ.get("RTC_EMU_DEFS"):
         pytest.skip("pinned for the default build configuration")
     for name, value in want.items():

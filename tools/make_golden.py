@@ -258,6 +258,16 @@ def parser_fixture():
     print("parser fixture:", len(PARSER_TEXTS), "texts")
 
 
+def headline():
+    """The headline scenes pinned to the reference itself (round 2): golden rays of the three 100k dragons (primary,
+    first-bounce secondary and random rays through librefprobe -> Scene::RayIntersection) and one larger converged
+    render of practice5_dragon_100k.  ~25 minutes on 8 cores: the reference visits ~10^4 nodes per ray here."""
+    rays_fixture("practice5_dragon_100k", 2, 6)          # 65,536 primary rays + as many secondary and random ones
+    rays_fixture("practice5_dragon_100k_glass", 4, 7)
+    rays_fixture("practice5_dragon_100k_metal", 4, 8)
+    render_fixture("practice5_dragon_100k", 96, 96, 512)
+
+
 def main():
     if not orclib.have_ref():
         raise SystemExit("oracle/_ref/librefprobe.so missing: run `make -C oracle` where /root/reference exists")
@@ -301,5 +311,7 @@ def dialects():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dialects":
         dialects()
+    elif len(sys.argv) > 1 and sys.argv[1] == "headline":
+        headline()
     else:
         main()

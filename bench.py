@@ -488,15 +488,17 @@ def build_rooflines(scene, args, cnt, stats, lanes, prof, ms_profiled, peaks):
              "units_per_launch": units / launches, "avg_launch_ms": per_launch_ms, "launches": launches,
              "share_of_step": ms / ms_profiled if ms_profiled > 0 else None,
              "munits_per_s_in_kernel": units / (ms * 1e-3) / 1e6 if ms > 0 else None}
-        if bound == "hbm" and n.get("dram_bytes_per_unit"):
-            # the same fraction on MEASURED DRAM traffic (ncu dram__bytes per unit of the committed launch list)
-            r["achieved_on_traffic"] = n["dram_bytes_per_unit"] * units / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        # Per-launch figures of the committed ncu launch list of this same command (profiles/traffic.json); the launches of a
+        # kernel are statistically alike from frame to frame, so "per launch" there and here mean the same work.
+        if bound == "hbm" and n.get("dram_bytes_per_launch") and per_launch_ms > 0:
+            # the same fraction on MEASURED DRAM traffic
+            r["achieved_on_traffic"] = n["dram_bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9
             r["frac_on_traffic"] = r["achieved_on_traffic"] / peak if peak else None
-        if n.get("warp_inst_per_unit") and peaks and ms > 0:
-            gw = n["warp_inst_per_unit"] * units / (ms * 1e-3) / 1e9
-            r["issue"] = {"warp_inst_per_unit": n["warp_inst_per_unit"], "achieved_gwinst_s": gw,
+        if n.get("warp_inst_per_launch") and peaks and per_launch_ms > 0:
+            gw = n["warp_inst_per_launch"] / (per_launch_ms * 1e-3) / 1e9
+            r["issue"] = {"warp_inst_per_unit": n["warp_inst_per_launch"] / max(units / launches, 1), "achieved_gwinst_s": gw,
                           "peak_gwinst_s": peaks["ffma_gwinst_s"], "frac": gw / peaks["ffma_gwinst_s"],
-                          "lanes_per_32_ncu": n.get("lanes_per_inst")}
+                          "lanes_per_32_ncu": n.get("lanes_per_inst"), "issue_active_pct_ncu": n.get("issue_active_pct")}
         if n.get("l1_wavefronts_pct"):
             r["l1_data_pipe_pct_ncu"] = n["l1_wavefronts_pct"]
         if key == "traverse":

@@ -15,8 +15,13 @@
 // recursion is then replayed on just those leaves, using lowest-common-ancestor queries on
 // the reference tree (DESIGN.md "Traversal").
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <future>
+#include <thread>
 #include <numeric>
 #include <stdexcept>
 
@@ -64,8 +69,16 @@ Aabb aabb_of_primitive(const Primitive& p) {
 // primitive indices; std::sort / std::partition are the very library routines the reference
 // calls, with an equivalent comparator, so equal keys end up in the same order as there.
 namespace {
+// levels of the two tree builds whose halves run concurrently: 2^levels tasks at most (RTC_BUILD_THREADS=1: serial)
+int build_parallel_levels() {
+    unsigned threads = std::thread::hardware_concurrency();
+    if (const char* v = std::getenv("RTC_BUILD_THREADS")) threads = (unsigned)std::atoi(v);
+    int levels = 0;
+    while (levels < 5 && (2u << levels) <= threads) ++levels;
+    return levels;
+}
+
 struct RefBuilder {
-    std::vector<RefNode>& nodes;
     std::vector<int32_t>& perm;
     const std::vector<Aabb>& box;         // per original primitive
     const std::vector<Primitive>& prims;  // original order
@@ -77,11 +90,15 @@ struct RefBuilder {
                   [P, axis](int32_t a, int32_t b) { return idx(P[a].pos, axis) < idx(P[b].pos, axis); });
     }
 
-    uint32_t build(uint32_t first, uint32_t last) {
+    // Appends the subtree of perm[first, last) to `out` in creation (pre-)order and returns the index of its root.
+    // The two halves of a node are independent (disjoint ranges of perm and cost): for the top `par` levels they are
+    // built concurrently into vectors of their own and appended left-then-right, which is exactly the order -- and
+    // therefore the node numbering -- of the reference's serial recursion.
+    uint32_t build(std::vector<RefNode>& out, uint32_t first, uint32_t last, int par) {
         Aabb all = empty_box();
         for (uint32_t i = first; i < last; ++i) grow(all, box[perm[i]]);
-        uint32_t me = (uint32_t)nodes.size();
-        nodes.push_back(RefNode{all, UINT32_MAX, UINT32_MAX, first, last - first});
+        uint32_t me = (uint32_t)out.size();
+        out.push_back(RefNode{all, UINT32_MAX, UINT32_MAX, first, last - first});
         if (last - first == 1) return me;
 
         float best[3] = {kInf, kInf, kInf};
@@ -114,10 +131,25 @@ struct RefBuilder {
                 break;
             }
         }
-        uint32_t l = build(first, cut);
-        nodes[me].left = l;
-        uint32_t r = build(cut, last);
-        nodes[me].right = r;
+        if (par > 0 && last - first >= 4096) {
+            std::vector<RefNode> lhs, rhs;
+            auto other = std::async(std::launch::async, [&] { build(lhs, first, cut, par - 1); });
+            build(rhs, cut, last, par - 1);
+            other.get();
+            for (std::vector<RefNode>* half : {&lhs, &rhs}) {
+                const uint32_t off = (uint32_t)out.size();
+                (half == &lhs ? out[me].left : out[me].right) = off;
+                for (RefNode n : *half) {
+                    if (n.left != UINT32_MAX) { n.left += off; n.right += off; }
+                    out.push_back(n);
+                }
+            }
+            return me;
+        }
+        uint32_t l = build(out, first, cut, 0);
+        out[me].left = l;
+        uint32_t r = build(out, cut, last, 0);
+        out[me].right = r;
         return me;
     }
 };
@@ -244,7 +276,6 @@ struct IndexBuilder {
     const std::vector<Unit>& units;
     std::vector<f4>& out;  // kIndexNodeF4 f4 (96 bytes) per 4-wide node
     std::vector<float> rarea;
-    uint32_t max_depth = 0;
     double slack = 0;  // absolute inflation of every child half-extent: 2^-20 of the scene size (set by HostScene::init)
 
     static uint32_t leaf_ref(const Unit& u) { return IREF_LEAF | (u.fast ? IREF_FAST : 0u) | ((u.count - 1) << 24) | u.first; }
@@ -277,9 +308,16 @@ struct IndexBuilder {
         scratch.resize(n);
         left_side.assign(n, 0);
     }
-    // returns the child reference for the units in [lo, hi) and the feasibility cone of that subtree
-    uint32_t build(uint32_t lo, uint32_t hi, uint32_t depth, Cone& cone) {
-        max_depth = std::max(max_depth, depth);
+    struct Bin {
+        Aabb box[2];
+        uint32_t ref[2];
+        Cone cone[2];
+    };
+    std::vector<Bin> tmp;
+    // Appends the binary subtree of the units in [lo, hi) to `out` (pre-order); returns its child reference (a leaf
+    // reference, or the index of its root in `out`) and the feasibility cone of the subtree.  As in RefBuilder the two
+    // sides of a split touch disjoint ranges of every array, and the top `par` levels build them concurrently.
+    uint32_t build(std::vector<Bin>& out, uint32_t lo, uint32_t hi, uint32_t depth, Cone& cone, int par) {
         if (hi - lo == 1) { cone = units[sorted[0][lo]].cone; return leaf_ref(units[sorted[0][lo]]); }
         // Split cost = sum over the two sides of P(a random ray enters the side) * units in it, with
         // P = surface of the box * fraction of directions inside the feasibility cone.  Candidate orders: the
@@ -323,29 +361,40 @@ struct IndexBuilder {
             uint32_t nl = lo, nr = 0;
             for (uint32_t i = lo; i < hi; ++i) {
                 if (left_side[order[i]]) order[nl++] = order[i];
-                else scratch[nr++] = order[i];
+                else scratch[lo + nr++] = order[i];
             }
-            std::copy(scratch.begin(), scratch.begin() + nr, order.begin() + nl);
+            std::copy(scratch.begin() + lo, scratch.begin() + lo + nr, order.begin() + nl);
         }
         for (uint32_t i = lo; i < best_cut; ++i) left_side[sorted[best_axis][i]] = 0;
         // binary node in a temporary tree; emit() collapses it to 4-wide nodes afterwards
-        uint32_t me = (uint32_t)tmp.size();
-        tmp.push_back(Bin{});
+        uint32_t me = (uint32_t)out.size();
+        out.push_back(Bin{});
         Aabb lb = bound(lo, best_cut), rb = bound(best_cut, hi);
         Cone lc, rc;
-        uint32_t lref = build(lo, best_cut, depth + 1, lc);
-        uint32_t rref = build(best_cut, hi, depth + 1, rc);
-        tmp[me] = Bin{{lb, rb}, {lref, rref}, {lc, rc}};
+        uint32_t lref, rref;
+        if (par > 0 && hi - lo >= 4096) {
+            std::vector<Bin> lhs, rhs;
+            auto other = std::async(std::launch::async, [&] { lref = build(lhs, lo, best_cut, depth + 1, lc, par - 1); });
+            rref = build(rhs, best_cut, hi, depth + 1, rc, par - 1);
+            other.get();
+            for (std::vector<Bin>* half : {&lhs, &rhs}) {
+                const uint32_t off = (uint32_t)out.size();
+                uint32_t& top = half == &lhs ? lref : rref;
+                if (!(top & IREF_LEAF)) top += off;
+                for (Bin b : *half) {
+                    for (uint32_t& r : b.ref) if (!(r & IREF_LEAF)) r += off;
+                    out.push_back(b);
+                }
+            }
+        } else {
+            lref = build(out, lo, best_cut, depth + 1, lc, 0);
+            rref = build(out, best_cut, hi, depth + 1, rc, 0);
+        }
+        out[me] = Bin{{lb, rb}, {lref, rref}, {lc, rc}};
         cone = merge_cones(lc, rc);
         return me;
     }
 
-    struct Bin {
-        Aabb box[2];
-        uint32_t ref[2];
-        Cone cone[2];
-    };
-    std::vector<Bin> tmp;
     uint32_t wide_depth = 0;
 
     // ---- optimal collapse of the binary tree into 4-wide nodes (dynamic programme over the binary tree).
@@ -498,7 +547,22 @@ static f4 pack(vec3 v, uint32_t bits) {
     return r;
 }
 
+namespace {
+// RTC_TIMING=1: phase times of the host scene build on stderr
+struct PhaseTimer {
+    bool on = std::getenv("RTC_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rtc timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 void HostScene::init() {
+    PhaseTimer timer;
     const uint32_t n = (uint32_t)prims.size();
     if (n >= IREF_MAX_PRIMS) throw std::runtime_error("scene has more than 2^24 primitives");
 
@@ -516,10 +580,11 @@ void HostScene::init() {
         for (uint32_t i = 0; i < n; ++i)
             if (original[i].type != PT_PLANE) boxes[i] = aabb_of_primitive(original[i]);
         nodes.reserve(2 * (size_t)nbvh);
-        RefBuilder rb{nodes, perm, boxes, original, std::vector<float>((size_t)nbvh + 1, 0.f)};
-        root = rb.build(0, nbvh);
+        RefBuilder rb{perm, boxes, original, std::vector<float>((size_t)nbvh + 1, 0.f)};
+        root = rb.build(nodes, 0, nbvh, build_parallel_levels());
     }
     for (uint32_t i = 0; i < n; ++i) prims[i] = original[perm[i]];
+    timer.lap("reference BVH (RefBuilder)");
 
     // ---- Scene::InitDistribution (src/scene.cpp:27-40)
     lights.clear();
@@ -576,6 +641,7 @@ void HostScene::init() {
         F.planes.push_back(pack(p.pos, rot_ident ? 1u : 0u));
     }
 
+    timer.lap("flatten primitives");
     // ---- reference tree: centre/half boxes (AABB_t::Intersect, src/bvh.cpp:89-93), depth, cuts
     const uint32_t nn = (uint32_t)nodes.size();
     F.rnodes.resize(2 * (size_t)nn);
@@ -620,6 +686,7 @@ void HostScene::init() {
         F.ubox[2 * (size_t)u.first + 1] = f4{u.box.mx.x, u.box.mx.y, u.box.mx.z, 0.f};
     }
 
+    timer.lap("reference nodes, units, cones");
     // ---- index BVH
     F.inodes.clear();
     F.iroot = IREF_NONE;
@@ -631,9 +698,12 @@ void HostScene::init() {
                 if (std::isfinite(v)) extent = std::max(extent, (double)std::fabs(v));
         ib.slack = extent * (1.0 / 1048576.0);
         ib.prepare();
+        timer.lap("index BVH: presort");
         Cone whole;
-        uint32_t broot = ib.build(0, (uint32_t)units.size(), 0, whole);
+        uint32_t broot = ib.build(ib.tmp, 0, (uint32_t)units.size(), 0, whole, build_parallel_levels());
+        timer.lap("index BVH: sweep build");
         F.iroot = (broot & IREF_LEAF) ? broot : ib.emit(broot, 1);
+        timer.lap("index BVH: collapse + emit");
         F.index_depth = ib.wide_depth;
     }
 
@@ -660,6 +730,7 @@ void HostScene::init() {
             }
         }
     }
+    timer.lap("LCA table");
 }
 
 }  // namespace rtc

@@ -9,6 +9,9 @@ import orclib
 from conftest import golden, scene_path
 
 RAY_SCENES = ["practice5_1", "practice5_2", "lights_mix", "practice5_dragon_10k", "rabbid"]
+# the headline scenes pinned to the reference itself (tools/make_golden.py headline): the oracle's node-by-node walk of the
+# reference tree costs ~10^4 node visits per ray at 100k triangles, so the CPU suite checks a strided subset of each set
+HEADLINE_SCENES = ["practice5_dragon_100k", "practice5_dragon_100k_glass", "practice5_dragon_100k_metal"]
 
 
 def bits(a):
@@ -174,3 +177,27 @@ def test_parser_quirks_match_reference(oracle_lib):
         oracle_lib.lib.orc_scene_free(h)
         i += 1
     assert i == 4
+
+
+@pytest.mark.parametrize("name", HEADLINE_SCENES)
+def test_headline_scene_structure_and_rays_bit_exact(oracle_scenes, name):
+    """The 100k dragons against golden vectors of the compiled reference: tree (node count, links checksum, box sums),
+    camera rays, and primitive id / t / normal of primary, first-bounce secondary and random rays, bit for bit."""
+    g = golden(name + "_rays")
+    s = oracle_scenes(name)
+    info = g["info"]
+    assert [s.width, s.height, s.ray_depth, s.samples, s.nprims, s.nbvh, s.nnodes, s.nlights] == info.tolist()
+    aabb, links, root = s.nodes()
+    crc = np.bitwise_xor.reduce((links.ravel().astype(np.uint64) * np.arange(1, links.size + 1, dtype=np.uint64)) & np.uint64(0xFFFFFFFF))
+    assert crc == g["node_links_crc"][0] and root == g["root"][0]
+    assert np.array_equal(aabb.astype(np.float64).sum(0), g["node_aabb_sum"])
+    o, d = s.camera_rays(g["xy"])
+    assert np.array_equal(bits(o), bits(g["cam_o"])) and np.array_equal(bits(d), bits(g["cam_d"]))
+    step = 16 if name == "practice5_dragon_100k" else 8
+    for kind, pre in (("cam", ""), ("sec", "sec_"), ("rnd", "rnd_")):
+        sel = slice(0, None, step)
+        pid, t, nrm, inter = s.intersect(g[kind + "_o"][sel], g[kind + "_d"][sel])
+        assert np.array_equal(pid, g[pre + "pid"][sel]), (kind, (pid != g[pre + "pid"][sel]).sum())
+        assert np.array_equal(bits(t), bits(g[pre + "t"][sel]))
+        assert np.array_equal(bits(nrm), bits(g[pre + "nrm"][sel]))
+        assert np.array_equal(inter, g[pre + "inter"][sel])

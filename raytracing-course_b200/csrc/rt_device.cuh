@@ -232,16 +232,27 @@ RT_D bool prim_hit_t(const DevScene& S, uint32_t prim, vec3 o, vec3 d, float& t)
     t = is.t;
     return ok;
 }
-// Primitive::Intersect, src/primitives.cpp:14-52 (normal back to world space, re-normalised)
+// Primitive::Intersect, src/primitives.cpp:14-52 (normal back to world space, re-normalised), on rows the caller has
+// already fetched: xp = xf_pos[prim] (position, type | flags), g0..g2 = geo0..2[prim].  k_shade issues those loads (and
+// the material rows) together as soon as it knows the primitive, instead of flags -> position -> geometry one after
+// the other (16 % of its stall samples sat on that chain).
 template <bool FAST = false, uint32_t FEAT = FE_ALL, bool FAST_NORMAL = FAST>
-RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect& out) {
-    uint32_t flags = prim_flags_for<FEAT>(S, prim);
-    to_local(S, prim, flags, o, d);
-    float4 g0 = ldg4(S.geo0 + prim);
+RT_D bool prim_intersect_rows(const DevScene& S, uint32_t prim, float4 xp, float4 g0, float4 g1, float4 g2, vec3 o, vec3 d, Isect& out) {
+    uint32_t flags = __float_as_uint(xp.w);
+    if (!(FEAT & FE_ROTATION)) flags |= PF_ROT_IDENT;
+    if (!(flags & PF_IDENT)) {  // to_local
+        o = o - ld3(xp);
+        if (!(flags & PF_ROT_IDENT)) {
+            float4 q4 = ldg4(S.xf_rot + prim);
+            quat qc;
+            qc.x = -q4.x; qc.y = -q4.y; qc.z = -q4.z; qc.w = q4.w;
+            o = rotate_exact(qc, o);
+            d = rotate_exact(qc, d);
+        }
+    }
     bool ok;
     const uint32_t type = flags & PF_TYPE_MASK;
     if (type == PT_TRIANGLE) {
-        float4 g1 = ldg4(S.geo1 + prim), g2 = ldg4(S.geo2 + prim);
         vec3 n = mk3(g0.w, g1.w, g2.w);
         bool interior;
         ok = isect_triangle(o, d, ld3(g0), ld3(g1), ld3(g2), n, out.t, interior);
@@ -263,6 +274,13 @@ RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect
     }
     out.n = rt_normalize<FAST_NORMAL>(out.n);
     return true;
+}
+template <bool FAST = false, uint32_t FEAT = FE_ALL, bool FAST_NORMAL = FAST>
+RT_D bool prim_intersect(const DevScene& S, uint32_t prim, vec3 o, vec3 d, Isect& out) {
+    const float4 xp = ldg4(S.xf_pos + prim), g0 = ldg4(S.geo0 + prim);
+    float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), g2 = g1;
+    if ((__float_as_uint(xp.w) & PF_TYPE_MASK) == PT_TRIANGLE) { g1 = ldg4(S.geo1 + prim); g2 = ldg4(S.geo2 + prim); }
+    return prim_intersect_rows<FAST, FEAT, FAST_NORMAL>(S, prim, xp, g0, g1, g2, o, d, out);
 }
 
 // ------------------------------------------------------------------------------- boxes

@@ -378,13 +378,18 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
             Isect is;
             vec3 o = ld3(o4), d = ld3(WF_LD(P.d + i));
             vec3 L;   // what this hit adds to the pixel: beta * (background | emission)
-            if (prim == HIT_MISS || !prim_intersect<false, FEAT, true>(S, prim, o, d, is)) {  // exact t, rsqrt normal
+            // every row of the winner at once (one round trip instead of flags -> position -> geometry -> material)
+            float4 xp = make_float4(0.f, 0.f, 0.f, 0.f), g0 = xp, g1 = xp, g2 = xp, m0 = xp, m1 = xp;
+            if (prim != HIT_MISS) {
+                xp = ldg4(S.xf_pos + prim); g0 = ldg4(S.geo0 + prim); g1 = ldg4(S.geo1 + prim); g2 = ldg4(S.geo2 + prim);
+                m0 = ldg4(S.mat0 + prim); m1 = ldg4(S.mat1 + prim);
+            }
+            if (prim == HIT_MISS || !prim_intersect_rows<false, FEAT, true>(S, prim, xp, g0, g1, g2, o, d, is)) {  // exact t, rsqrt normal
                 L = beta * mk3(S.bg.x, S.bg.y, S.bg.z);  // src/scene.cpp:92-94
             } else {
                 bool interior = is.interior != 0;
                 vec3 normal = is.n;
                 vec3 p = o + is.t * d;
-                float4 m0 = ldg4(S.mat0 + prim), m1 = ldg4(S.mat1 + prim);
                 vec3 col = ld3(m0);
                 L = beta * ld3(m1);
                 uint32_t material = __float_as_uint(m0.w);
@@ -450,23 +455,31 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
             if (L.x != 0.f || L.y != 0.f || L.z != 0.f) deposit(accum4, pixel, L);
         }
         unsigned mask = __ballot_sync(kFullMask, alive);
-        uint32_t enters = 0;
-        uint32_t dst = 0;
         if (mask) {
-            uint32_t base = 0;
+            // Both queue reservations are in flight while the next ray's pre_step is computed: the results of the two
+            // atomics are first needed by the stores at the very end (12 % of the kernel's stall samples sat on them
+            // when each was awaited where it was issued).
+            const uint32_t lt = (1u << lane) - 1u;
+            uint32_t base = 0, tbase = 0;
             if (lane == 0) base = atomicAdd(qout, (uint32_t)__popc(mask));
+            // first part of the next Scene::RayIntersection, while the ray is still in registers
+            float cd = 0.f;
+            uint32_t id = HIT_MISS, enters = 0;
+            if (alive) enters = pre_step<FEAT>(S, no, nd, cd, id);
+            const unsigned emask = __ballot_sync(kFullMask, enters != 0);
+            if (emask && lane == 0) tbase = atomicAdd(tq_count, (uint32_t)__popc(emask));
             base = __shfl_sync(kFullMask, base, 0);
+            const uint32_t dst = base + __popc(mask & lt);
             if (alive) {
-                dst = base + __popc(mask & ((1u << lane) - 1u));
-                // first part of the next Scene::RayIntersection, while the ray is still in registers
-                float cd; uint32_t id;
-                enters = pre_step<FEAT>(S, no, nd, cd, id);
                 WF_ST(N.o + dst, make_float4(no.x, no.y, no.z, __uint_as_float(sample)));
                 WF_ST(N.d + dst, make_float4(nd.x, nd.y, nd.z, cd));
                 WF_ST(N.beta + dst, make_float4(beta.x, beta.y, beta.z, __uint_as_float(pixel)));
                 WF_ST(HN.id + dst, id);
             }
-            enqueue(enters, dst, tq, tq_count, lane);
+            if (emask) {
+                tbase = __shfl_sync(kFullMask, tbase, 0);
+                if (enters) WF_ST(tq + tbase + __popc(emask & lt), dst | (enters << kTqSlotBits));
+            }
         }
     }
 }

@@ -120,7 +120,7 @@ struct rtc_scene {
         DevBuf<float4> path[2][3];           // two ping-pong sets of (origin | sample, direction | closest plane, throughput | pixel)
         DevBuf<uint32_t> hit_id[2];
         DevBuf<uint32_t> trav_queue;         // ray indices handed to k_traverse
-        DevBuf<uint32_t> queue;              // 3 x kMaxDepthSlots words: path counts, traverse counts, cursors
+        DevBuf<uint32_t> queue;              // 4 x kMaxDepthSlots words: path counts (front, back per bounce), traverse counts, cursors
         void release() {
             for (auto& set : path) for (auto& b : set) b.release();
             for (auto& b : hit_id) b.release();
@@ -425,7 +425,7 @@ int ensure_wavefront(rtc_scene* s, uint64_t cap, int nlanes) {
         for (auto& set : l.path) for (auto& b : set) CU(b.ensure(cap));
         for (auto& b : l.hit_id) CU(b.ensure(cap));
         CU(l.trav_queue.ensure(cap));
-        CU(l.queue.ensure(3 * kMaxDepthSlots));
+        CU(l.queue.ensure(4 * kMaxDepthSlots));
     }
     return RTC_OK;
 }
@@ -545,7 +545,7 @@ int rtc_intersect_dev(rtc_scene* s, long n, const float* o_dev, const float* d_d
     if ((uint64_t)n > (1ull << 28)) return fail(RTC_ERR_ARG, "too many rays in one call (limit 2^28)");
     rtc_scene::Probe& pb = s->probe;
     CU(pb.ray[0].ensure((size_t)n)); CU(pb.ray[1].ensure((size_t)n));
-    CU(pb.hit.ensure((size_t)n)); CU(pb.tq.ensure((size_t)n)); CU(pb.q.ensure(4));
+    CU(pb.hit.ensure((size_t)n)); CU(pb.tq.ensure((size_t)n)); CU(pb.q.ensure(4));   // q: rays (front, back = 0), traverse count, cursor
     cudaStream_t st = (cudaStream_t)stream;
     PathSoA P{pb.ray[0].p, pb.ray[1].p, nullptr};
     HitSoA H{pb.hit.p};
@@ -558,8 +558,8 @@ int rtc_intersect_dev(rtc_scene* s, long n, const float* o_dev, const float* d_d
     launch_pack_rays(c, n, o_dev, d_dev, P, q);
     if (mode == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, P, H, q, (uint32_t)n);
     else {
-        launch_pre(c, S, P, H, q, (uint32_t)n, pb.tq.p, q + 1);
-        launch_traverse(c, S, P, H, (uint32_t)n, pb.tq.p, q + 1, q + 2, false, s->stats.p);
+        launch_pre(c, S, P, H, q, (uint32_t)n, pb.tq.p, q + 2);
+        launch_traverse(c, S, P, H, (uint32_t)n, pb.tq.p, q + 2, q + 3, false, s->stats.p);
     }
     launch_unpack_hits(c, S, n, P, H, id_dev, t_dev, normal_dev, interior_dev);
     CU(cudaEventRecord(s->arena_idle[s->arena_cur], st));
@@ -732,10 +732,10 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         rtc_scene::Lane& L = s->lanes[batch % nlanes];
         cudaStream_t st = L.stream;
         LaunchCtx c{st, s->sms};
-        uint32_t* tqc = L.queue.p + kMaxDepthSlots;        // rays queued for k_traverse, per bounce
-        uint32_t* cursor = L.queue.p + 2 * kMaxDepthSlots; // k_traverse work cursors, per bounce
+        uint32_t* tqc = L.queue.p + 2 * kMaxDepthSlots;    // rays queued for k_traverse, per bounce
+        uint32_t* cursor = L.queue.p + 3 * kMaxDepthSlots; // k_traverse work cursors, per bounce
         uint32_t count = (uint32_t)((total - first) < cap ? (total - first) : cap);
-        CU(cudaMemsetAsync(L.queue.p, 0, 3 * kMaxDepthSlots * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(L.queue.p, 0, 4 * kMaxDepthSlots * sizeof(uint32_t), st));
         PathSoA cur{L.path[0][0].p, L.path[0][1].p, L.path[0][2].p};
         PathSoA nxt{L.path[1][0].p, L.path[1][1].p, L.path[1][2].p};
         HitSoA hcur{L.hit_id[0].p}, hnxt{L.hit_id[1].p};
@@ -745,11 +745,11 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
         s->launches++;
         for (uint32_t b = 1; b <= depth; ++b) {
             s->span_begin(1, st);
-            if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, L.queue.p + (b - 1), count);
+            if (s->traversal == RTC_TRAVERSAL_REFTREE) launch_extend_reftree(c, S, cur, hcur, L.queue.p + 2 * (b - 1), count);
             else launch_traverse(c, S, cur, hcur, count, L.trav_queue.p, tqc + (b - 1), cursor + (b - 1), s->count_visits, s->stats.p);
             s->span_end(st);
             s->span_begin(2, st);
-            launch_shade(c, S, cur, hcur, nxt, hnxt, L.queue.p + (b - 1), L.queue.p + b, L.trav_queue.p, tqc + b, count,
+            launch_shade(c, S, cur, hcur, nxt, hnxt, L.queue.p + 2 * (b - 1), L.queue.p + 2 * b, L.trav_queue.p, tqc + b, count,
                          accum4.p, b, seed);
             s->span_end(st);
             s->launches += 2;

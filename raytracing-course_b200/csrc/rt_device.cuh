@@ -827,11 +827,16 @@ RT_D vec3 sample_ellipsoid(const DevScene& S, uint32_t prim, const Rng& g, vec3 
     return smp;
 }
 // Distribution::SampleMix, src/distributions.cpp:385-399
+// The coin of Distribution::SampleMix for the shading at slot `g.slot`: true = a light is sampled, false = the cosine lobe.
+RT_D bool mix_picks_light(const DevScene& S, const Rng& g) { return S.nlights != 0 && !(u01(g.block(0).x) <= 0.5f); }
+// `known`: -1 = toss the coin here; 0 / 1 = the caller already knows it came up cosine / light (k_shade keeps the two
+// kinds of rays in different warps, rt_kernels.cu) -- the cosine side then never computes block 0.
 template <uint32_t FEAT = FE_ALL>
-RT_D vec3 mix_sample(const DevScene& S, const Rng& g, vec3 x, vec3 n) {
+RT_D vec3 mix_sample(const DevScene& S, const Rng& g, vec3 x, vec3 n, int known = -1) {
+    if (known == 0) return sample_cosine(g, n);
     uint4 b0 = g.block(0);
     float flip = u01(b0.x);
-    if (S.nlights == 0 || flip <= 0.5f) return sample_cosine(g, n);
+    if (known < 0 && (S.nlights == 0 || flip <= 0.5f)) return sample_cosine(g, n);
     float fid = u01(b0.y);
     uint32_t id = (uint32_t)floorf(fid * (float)S.nlights);
     uint32_t prim = (uint32_t)__ldg(S.lights + id);

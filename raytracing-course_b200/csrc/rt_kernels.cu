@@ -70,6 +70,29 @@ RT_D void enqueue(uint32_t rootmask, uint32_t i, uint32_t* tq, uint32_t* tq_coun
     }
 }
 
+// A path queue has two ends (round 2).  A surviving path is written to the FRONT when the mix distribution of its next
+// shading will sample the cosine lobe, to the BACK (slots cap - 1, cap - 2, ...) when it will sample a light: the coin is
+// a pure function of (seed, pixel, sample, bounce), so it can be tossed when the ray is made.  k_shade then walks the
+// front and the back in whole warps, and a warp runs ONE of the two sampling codes instead of both with half its lanes
+// masked (k_shade was bound by issue slots at 20 of 32 lanes).  q[0] = paths at the front, q[1] = paths at the back.
+struct QueueView {
+    uint32_t n_front, n_back, front_padded, total;   // total = both parts rounded up to whole warps
+};
+RT_D QueueView queue_view(const uint32_t* q) {
+    QueueView v;
+    v.n_front = q[0]; v.n_back = q[1];
+    v.front_padded = (v.n_front + 31u) & ~31u;
+    v.total = v.front_padded + ((v.n_back + 31u) & ~31u);
+    return v;
+}
+// virtual index (thread's position in the walk) -> slot; returns false for the padding lanes
+RT_D bool queue_slot(const QueueView& v, uint32_t at, uint32_t cap, uint32_t& slot, bool& back) {
+    back = at >= v.front_padded;
+    const uint32_t j = back ? at - v.front_padded : at;
+    slot = back ? cap - 1u - j : j;
+    return j < (back ? v.n_back : v.n_front);
+}
+
 // ------------------------------------------------------------------------------- generate
 // Scene::Sample's jitter + Camera::GetToRay (src/scene.cpp:189-200): one thread per path.
 // Path ids run sample-major over the image: consecutive threads = consecutive pixels of a row.
@@ -317,9 +340,11 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
 }
 
 // The node-by-node twin (RTC_TRAVERSAL_REFTREE): planes + the reference's own tree, one thread per ray.
-__global__ void __launch_bounds__(128) k_extend_reftree(DevScene S, PathSoA P, HitSoA H, const uint32_t* qcount) {
-    const uint32_t count = *qcount;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(128) k_extend_reftree(DevScene S, PathSoA P, HitSoA H, const uint32_t* q, uint32_t cap) {
+    const QueueView view = queue_view(q);
+    for (uint32_t at = blockIdx.x * blockDim.x + threadIdx.x; at < view.total; at += gridDim.x * blockDim.x) {
+        uint32_t i; bool back;
+        if (!queue_slot(view, at, cap, i, back)) continue;
         vec3 o = ld3(WF_LD(P.o + i)), d = ld3(WF_LD(P.d + i));
         float closest;
         int id;
@@ -361,16 +386,20 @@ RT_D void deposit(float4* accum4, uint32_t pixel, vec3 L) {
 template <bool HW3, uint32_t FEAT>
 __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_ELLIPSOID)) ? RTC_SHADE_MIN_BLOCKS_FULL : RTC_SHADE_MIN_BLOCKS_LEAN) k_shade(DevScene S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                                                 uint32_t* qout, uint32_t* tq, uint32_t* tq_count, float4* accum4, uint32_t bounce,
-                                                uint32_t seed) {
-    const uint32_t count = *qin;
+                                                uint32_t seed, uint32_t cap) {
+    const QueueView view = queue_view(qin);
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t rounded = (count + 31u) & ~31u;
     const float eps = S.eps;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+    // camera paths (bounce 1) arrive unsorted; from then on the end of the queue a path sits at tells its coin
+    const bool sorted_in = bounce > 1 && !HW3;
+    // the paths written here are shaded with sampling at bounce + 1 only if that is below RAY_DEPTH
+    const bool sort_out = !HW3 && S.nlights != 0 && bounce + 1 < S.ray_depth;
+    for (uint32_t at = blockIdx.x * blockDim.x + threadIdx.x; at < view.total; at += gridDim.x * blockDim.x) {
         bool alive = false;
         vec3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0), beta = mk3(0, 0, 0);
         uint32_t pixel = 0, sample = 0;
-        if (i < count) {
+        uint32_t i; bool back;
+        if (queue_slot(view, at, cap, i, back)) {
             const float4 b4 = WF_LD(P.beta + i), o4 = WF_LD(P.o + i);
             beta = ld3(b4);
             pixel = __float_as_uint(b4.w); sample = __float_as_uint(o4.w);
@@ -404,7 +433,7 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
                         alive = true;
                     } else if (material == MAT_DIFFUSE) {
                         vec3 p_outer = p + eps * normal;
-                        vec3 dir = mix_sample<FEAT>(S, g, p_outer, normal);
+                        vec3 dir = mix_sample<FEAT>(S, g, p_outer, normal, sorted_in ? (back ? 1 : 0) : -1);
                         float cs = dot(dir, normal);
                         if (cs > 0.f) {
                             float pw = mix_pdf<FEAT>(S, p_outer, normal, dir);
@@ -460,16 +489,23 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
             // atomics are first needed by the stores at the very end (12 % of the kernel's stall samples sat on them
             // when each was awaited where it was issued).
             const uint32_t lt = (1u << lane) - 1u;
-            uint32_t base = 0, tbase = 0;
-            if (lane == 0) base = atomicAdd(qout, (uint32_t)__popc(mask));
+            // which end of the next queue: the coin of the NEXT shading (slot bounce + 1), tossed now
+            bool to_back = false;
+            if (sort_out && alive) to_back = mix_picks_light(S, Rng{seed, pixel, sample, bounce + 1});
+            const unsigned bmask = __ballot_sync(kFullMask, to_back), fmask = mask & ~bmask;
+            unsigned long long both = 0;   // one 64-bit reservation: front count in the low word, back count in the high word
+            uint32_t tbase = 0;
+            if (lane == 0) both = atomicAdd(reinterpret_cast<unsigned long long*>(qout),
+                                            (unsigned long long)__popc(fmask) | ((unsigned long long)__popc(bmask) << 32));
             // first part of the next Scene::RayIntersection, while the ray is still in registers
             float cd = 0.f;
             uint32_t id = HIT_MISS, enters = 0;
             if (alive) enters = pre_step<FEAT>(S, no, nd, cd, id);
             const unsigned emask = __ballot_sync(kFullMask, enters != 0);
             if (emask && lane == 0) tbase = atomicAdd(tq_count, (uint32_t)__popc(emask));
-            base = __shfl_sync(kFullMask, base, 0);
-            const uint32_t dst = base + __popc(mask & lt);
+            both = __shfl_sync(kFullMask, both, 0);
+            const uint32_t dst = to_back ? cap - 1u - ((uint32_t)(both >> 32) + __popc(bmask & lt))
+                                         : (uint32_t)both + __popc(fmask & lt);
             if (alive) {
                 WF_ST(N.o + dst, make_float4(no.x, no.y, no.z, __uint_as_float(sample)));
                 WF_ST(N.d + dst, make_float4(nd.x, nd.y, nd.z, cd));
@@ -487,7 +523,7 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
 // totals: stats[0] += paths, stats[1] += rays, stats[3] += 1 batch, stats[7] += rays sent to k_traverse
 __global__ void k_tally(const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     unsigned long long rays = 0, queued = 0;
-    for (uint32_t b = 0; b < ray_depth; ++b) { rays += q[b]; queued += tqc[b]; }
+    for (uint32_t b = 0; b < ray_depth; ++b) { rays += q[2 * b] + q[2 * b + 1]; queued += tqc[b]; }
     // one k_tally per batch on each lane's own stream: two of them may run at the same time
     atomicAdd(stats + 0, (unsigned long long)q[0]);
     atomicAdd(stats + 1, rays);
@@ -633,14 +669,14 @@ void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H,
     if (count_visits) k_traverse<true><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, stats);
     else k_traverse<false><<<grid, 128, 0, c.stream>>>(S, P, H, tq, tq_count, cursor, stats);
 }
-void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count) {
-    k_extend_reftree<<<grid_for(max_count, 128, c.sms, 16), 128, 0, c.stream>>>(S, P, H, qcount);
+void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* q, uint32_t cap) {
+    k_extend_reftree<<<grid_for(cap, 128, c.sms, 16), 128, 0, c.stream>>>(S, P, H, q, cap);
 }
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                   uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float4* accum4, uint32_t bounce,
                   uint32_t seed) {
     const int grid = grid_for(max_count, RTC_SHADE_THREADS, c.sms, 2048 / RTC_SHADE_THREADS);
-#define RTC_SHADE(HW3, FEAT) k_shade<HW3, FEAT><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum4, bounce, seed)
+#define RTC_SHADE(HW3, FEAT) k_shade<HW3, FEAT><<<grid, RTC_SHADE_THREADS, 0, c.stream>>>(S, P, H, N, HN, qin, qout, tq, tq_count, accum4, bounce, seed, max_count)
     // the smallest instantiation that covers the scene's features (DevScene::features)
 #ifdef RTC_SHADE_NO_SPECIALISATION
     const uint32_t feat = FE_ALL;

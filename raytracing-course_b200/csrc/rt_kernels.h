@@ -21,7 +21,7 @@ void launch_pre(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, cons
                 uint32_t* tq, uint32_t* tq_count);
 void launch_traverse(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, uint32_t max_count, const uint32_t* tq,
                      const uint32_t* tq_count, uint32_t* cursor, bool count_visits, unsigned long long* stats);
-void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* qcount, uint32_t max_count);
+void launch_extend_reftree(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, const uint32_t* q, uint32_t cap);
 // shading of queue P with hits H; survivors go to queue N with their pre_step results in HN / tq
 void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, PathSoA N, HitSoA HN, const uint32_t* qin,
                   uint32_t* qout, uint32_t* tq, uint32_t* tq_count, uint32_t max_count, float4* accum4, uint32_t bounce,

@@ -215,7 +215,8 @@ def test_render_sample_exact_vs_oracle(rtc, oracle_lib, name, w, h, spp):
 
 @pytest.mark.parametrize("name,w,h,spp", [("practice5_1", 64, 48, 256), ("practice5_2", 64, 48, 1024), ("lights_mix", 48, 32, 1024),
                                           ("practice5_dragon_10k", 64, 64, 256), ("practice5_dragon_10k", 128, 128, 512), ("rabbid", 88, 88, 256),
-                                          ("practice5_dragon_100k", 48, 48, 128), ("practice5_dragon_100k_glass", 48, 48, 128),
+                                          ("practice5_dragon_100k", 48, 48, 128), ("practice5_dragon_100k", 96, 96, 512),
+                                          ("practice5_dragon_100k_glass", 48, 48, 128),
                                           ("practice5_dragon_100k_metal", 48, 48, 128)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_render_statistically_matches_reference(rtc, name, w, h, spp, mode):

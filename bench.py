@@ -74,13 +74,14 @@ def live_peaks(device):
     is being benchmarked; the committed copy of an earlier run (profiles/r02_peaks.json) if the library is missing."""
     so = os.path.join(ROOT, "tools", "peaks", "libpeaks.so")
     keys = ["l2_gather96_gbs", "l2_chase96_gbs", "l2_chase96_ns_per_fetch", "ffma_gwinst_s", "alu_gwinst_s",
-            "mixed_gwinst_s", "sm_mhz_seen", "copy_gbs", "sms", "fp32_tflops"]
+            "mixed_gwinst_s", "unused", "copy_gbs", "sms", "fp32_tflops"]
     try:
         lib = ctypes.CDLL(so)
         lib.rtc_peaks_measure.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
         out = (ctypes.c_double * 10)()
         if lib.rtc_peaks_measure(device, 36.0, out) == 0:
             d = dict(zip(keys, [float(v) for v in out]))
+            d.pop("unused", None)
             d["source"] = "measured live (tools/peaks)"
             return d
     except OSError:

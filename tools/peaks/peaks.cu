@@ -158,7 +158,7 @@ double best_ms(F launch, int reps) {
 // out[0] L2 gather GB/s (96-byte records, table_mb MB table, independent gathers)
 // out[1] the same with one dependent chain per thread (GB/s) and out[2] its latency per fetch in ns
 // out[3] FFMA warp-instructions / s (G), out[4] ALU-mix warp-instructions / s (G), out[5] interleaved (G)
-// out[6] SM clock seen by the FFMA kernel (MHz), out[7] streaming copy GB/s (read + write), out[8] SM count
+// out[6] unused, out[7] streaming copy GB/s (read + write), out[8] SM count
 // out[9] FP32 TFLOP/s of the FFMA kernel
 extern "C" int rtc_peaks_measure(int device, double table_mb, double out[10]) {
     if (cudaSetDevice(device) != cudaSuccess) return 1;
@@ -195,10 +195,6 @@ extern "C" int rtc_peaks_measure(int device, double table_mb, double out[10]) {
         const double winst = (double)grid * 8 * iters * K_FFMA_LOOP_INSTR;   // warps x instructions (64 FFMA + loop control)
         out[3] = winst / (ms * 1e-3) / 1e9;
         out[9] = (double)grid * 8 * iters * 64 * 32 * 2 / (ms * 1e-3) / 1e12;
-        long long cyc = 0;
-        cudaMemcpy(&cyc, clocks, sizeof cyc, cudaMemcpyDeviceToHost);
-        // clock64 over the loop of block 0 against the kernel's duration: a lower bound of the SM clock
-        out[6] = (double)cyc / (ms * 1e-3) / 1e6;
         ms = best_ms([&] { k_alu<<<grid, 256>>>(iters, sink); }, 5);
         out[4] = (double)grid * 8 * iters * K_ALU_LOOP_INSTR / (ms * 1e-3) / 1e9;
         ms = best_ms([&] { k_mixed<<<grid, 256>>>(iters, sink); }, 5);
@@ -226,9 +222,9 @@ int main(int argc, char** argv) {
     int rc = rtc_peaks_measure(0, mb, out);
     if (rc) { std::fprintf(stderr, "peaks: failed (%d)\n", rc); return 1; }
     std::printf("{\"table_mb\": %.1f, \"l2_gather96_gbs\": %.1f, \"l2_chase96_gbs\": %.1f, \"l2_chase96_ns_per_fetch\": %.1f, "
-                "\"ffma_gwinst_s\": %.1f, \"alu_gwinst_s\": %.1f, \"mixed_gwinst_s\": %.1f, \"sm_mhz_seen\": %.0f, "
+                "\"ffma_gwinst_s\": %.1f, \"alu_gwinst_s\": %.1f, \"mixed_gwinst_s\": %.1f, "
                 "\"copy_gbs\": %.1f, \"sms\": %d, \"fp32_tflops\": %.2f}\n",
-                mb, out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7], (int)out[8], out[9]);
+                mb, out[0], out[1], out[2], out[3], out[4], out[5], out[7], (int)out[8], out[9]);
     return 0;
 }
 #endif

@@ -472,6 +472,7 @@ struct IndexBuilder {
         }
         uint32_t me = (uint32_t)(out.size() / kIndexNodeF4);
         out.resize(out.size() + kIndexNodeF4, f4{0, 0, 0, 0});
+        bool any_cone = false;
         // one block of 4 children after the other (a node of width 8 is two blocks of the same layout)
         for (int blk = 0; blk < W / 4; ++blk) {
             uint16_t hv[6][4];
@@ -513,6 +514,7 @@ struct IndexBuilder {
                         cv[0][i] = half_bits_rn((float)c.ax); cv[1][i] = half_bits_rn((float)c.ay); cv[2][i] = half_bits_rn((float)c.az);
                         cv[3][i] = half_down((float)thr);
                         if (cv[3][i] & 0x8000u) cv[3][i] = 0;
+                        if (cv[3][i] != 0) any_cone = true;
                     }
                 }
                 refs[i] = IREF_NONE;
@@ -536,7 +538,7 @@ struct IndexBuilder {
             out[kIndexNodeF4 * me + kIndexBlockF4 * blk + 5] = bits4(cw[4], cw[5], cw[6], cw[7]);
 #endif
         }
-        return me;
+        return any_cone ? me : (me | IREF_NOCONE);
     }
 };
 }  // namespace

@@ -12,6 +12,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_scene.h"
@@ -991,8 +992,9 @@ int rtc_render_u8_multi(rtc_scene* s, const int* devices, int ndev, uint32_t see
     std::memset(&A, 0, sizeof A);
     A.n = ndev;
     rtc_scene* head = ctx[0];
-    // every device renders its sample range into its own buffer on its own stream
-    for (int i = 0; i < ndev; ++i) {
+    // every device renders its sample range into its own buffer on its own stream; the ~30 launches of a device's
+    // share are issued by a host thread of its own (one thread issuing for 8 devices took 1.1 of a 3.9 ms frame)
+    auto issue = [&](int i) -> int {
         rtc_scene* c = ctx[i];
         CU(cudaSetDevice(c->device));
         if (!c->multi_stream) CU(cudaStreamCreateWithFlags(&c->multi_stream, cudaStreamNonBlocking));
@@ -1000,9 +1002,23 @@ int rtc_render_u8_multi(rtc_scene* s, const int* devices, int ndev, uint32_t see
         CU(c->accum.ensure(nvalues));
         CU(cudaMemsetAsync(c->accum.p, 0, nvalues * sizeof(float), c->multi_stream));
         const uint32_t lo = (uint32_t)((uint64_t)i * samples / ndev), hi = (uint32_t)((uint64_t)(i + 1) * samples / ndev);
-        if ((rc = rtc_render_accumulate(c, seed, lo, hi - lo, c->accum.p, c->multi_stream))) return rc;
+        int r = rtc_render_accumulate(c, seed, lo, hi - lo, c->accum.p, c->multi_stream);
+        if (r) return r;
         CU(cudaEventRecord(c->multi_done, c->multi_stream));
-        A.p[i] = c->accum.p;
+        return RTC_OK;
+    };
+    {
+        std::vector<int> rcs((size_t)ndev, RTC_OK);
+        std::vector<std::string> errs((size_t)ndev);
+        std::vector<std::thread> workers;
+        for (int i = 1; i < ndev; ++i)
+            workers.emplace_back([&, i] { rcs[i] = issue(i); if (rcs[i]) errs[i] = g_error; });   // g_error is per thread
+        rcs[0] = issue(0);
+        for (std::thread& w : workers) w.join();
+        for (int i = 0; i < ndev; ++i) {
+            if (rcs[i]) return i == 0 ? rcs[0] : fail(rcs[i], errs[i]);
+            A.p[i] = ctx[i]->accum.p;
+        }
     }
     // the head device reads the others' buffers in place (peer access), or copies them over when it cannot
     CU(cudaSetDevice(head->device));

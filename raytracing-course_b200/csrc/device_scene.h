@@ -52,7 +52,7 @@ inline void fill_dev_scalars(const HostScene& host, DevScene& S) {
     S.root = host.root; S.iroot = host.flat.iroot; S.lca_levels = host.flat.lca_levels;
     for (int c = 0; c < 4; ++c) S.iroot_ref[c] = IREF_NONE;
     if (host.flat.iroot != IREF_NONE && !(host.flat.iroot & IREF_LEAF)) {
-        const f4& refs = host.flat.inodes[kIndexNodeF4 * (size_t)host.flat.iroot + 3];   // words 12..15 of the node
+        const f4& refs = host.flat.inodes[kIndexNodeF4 * (size_t)(host.flat.iroot & IREF_NODE_MASK) + 3];   // words 12..15 of the node
         memcpy(S.iroot_ref, &refs, sizeof S.iroot_ref);
     }
     S.nlights = (uint32_t)host.lights.size(); S.ref_depth = host.flat.ref_depth;

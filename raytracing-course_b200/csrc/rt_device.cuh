@@ -528,7 +528,7 @@ RT_D uint32_t cone_cull_pair(ConeDir dn, float wx, float wy, float wz, float wt)
 #endif
 }
 // one block of 4 children: boxes, refs, cones (ref / hit point at the block's 4 entries of the NodeVisit)
-RT_D void index_visit_block(const float4* nd, vec3 inv, vec3 oi, ConeDir dn, uint32_t* ref, bool* hit) {
+RT_D void index_visit_block(const float4* nd, bool nocone, vec3 inv, vec3 oi, ConeDir dn, uint32_t* ref, bool* hit) {
     float4 q0, q1, q2, q3;
     ldg8(nd, q0, q1);
     ldg8(nd + 2, q2, q3);
@@ -552,8 +552,10 @@ RT_D void index_visit_block(const float4* nd, vec3 inv, vec3 oi, ConeDir dn, uin
     slab(ax23.y, ay23.y, az23.y, bx23.y, by23.y, bz23.y, inv, oi, ref[3], hit[3], tc);
 #endif
 #if RTC_NODE_CONES
-    float4 q4, q5;
-    ldg8(nd + 4, q4, q5);  // axis.x[0..3] axis.y[0..3] | axis.z[0..3] threshold[0..3]
+    // axis.x[0..3] axis.y[0..3] | axis.z[0..3] threshold[0..3]; a node without cones (IREF_NOCONE in the reference that
+    // led here) is tested against all-zero thresholds = nothing culled, and one scattered 32-byte load is saved
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), q5 = q4;
+    if (!nocone) ldg8(nd + 4, q4, q5);
     const uint32_t c01 = cone_cull_pair(dn, q4.x, q4.z, q5.x, q5.z), c23 = cone_cull_pair(dn, q4.y, q4.w, q5.y, q5.w);
     hit[0] = hit[0] && !(c01 & 1u); hit[1] = hit[1] && !(c01 >> 16);
     hit[2] = hit[2] && !(c23 & 1u); hit[3] = hit[3] && !(c23 >> 16);
@@ -562,10 +564,11 @@ RT_D void index_visit_block(const float4* nd, vec3 inv, vec3 oi, ConeDir dn, uin
 #endif
 }
 RT_D NodeVisit index_visit(const DevScene& S, uint32_t node, vec3 inv, vec3 oi, ConeDir dn) {
-    const float4* nd = S.inodes + kIndexNodeF4 * (size_t)node;
+    const float4* nd = S.inodes + kIndexNodeF4 * (size_t)(node & IREF_NODE_MASK);
+    const bool nocone = (node & IREF_NOCONE) != 0;
     NodeVisit v;
 #pragma unroll
-    for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) index_visit_block(nd + kIndexBlockF4 * blk, inv, oi, dn, v.ref + 4 * blk, v.hit + 4 * blk);
+    for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) index_visit_block(nd + kIndexBlockF4 * blk, nocone, inv, oi, dn, v.ref + 4 * blk, v.hit + 4 * blk);
     return v;
 }
 // closest primitive of one reference leaf (strict <: the first one wins ties, src/bvh.cpp:206-211)

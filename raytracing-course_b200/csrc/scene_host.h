@@ -139,6 +139,10 @@ struct HostScene {
 // child reference encoding of the index BVH
 constexpr uint32_t IREF_LEAF = 0x80000000u;
 constexpr uint32_t IREF_NONE = 0xFFFFFFFFu;
+// in a reference to an INNER node (bit 31 clear): none of the node's children has a direction cone, the visit skips
+// the third 32-byte load (the upper levels of the tree: cones only bite in the lowest five)
+constexpr uint32_t IREF_NOCONE = 0x40000000u;
+constexpr uint32_t IREF_NODE_MASK = 0x00FFFFFFu;   // index of an inner node inside its reference
 constexpr uint32_t IREF_FAST = 0x40000000u;     // leaf = one triangle with pos 0 and identity rotation
 constexpr uint32_t IREF_MAX_LEAF_PRIMS = 64;   // 6 bits (24..29)
 constexpr uint32_t IREF_MAX_PRIMS = 1u << 24;

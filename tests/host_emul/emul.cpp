@@ -179,7 +179,7 @@ int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t*
             const uint32_t* w = (const uint32_t*)&F.inodes[kIndexNodeF4 * i + kIndexBlockF4 * (c / 4)];
             uint32_t r = w[12 + (c & 3)];
             if (r == IREF_NONE || (r & IREF_LEAF)) continue;
-            hh = std::max(hh, height[r] + 1);
+            hh = std::max(hh, height[r & IREF_NODE_MASK] + 1);
         }
         height[i] = hh;
     }
@@ -195,7 +195,7 @@ int emu_index_profile(void* h, long n, const float* o, const float* d, uint64_t*
             uint32_t node = st.back();
             st.pop_back();
             NodeVisit box = index_visit(S, node, inv, oi, none), both = index_visit(S, node, inv, oi, dn);
-            int hh = std::min(height[node], 31);
+            int hh = std::min(height[node & IREF_NODE_MASK], 31);
             out[3 * hh] += 1;
             for (int c = 0; c < (int)kNodeWidth; ++c) {
                 out[3 * hh + 1] += box.hit[c];
@@ -228,7 +228,7 @@ int emu_index_check(void* h, uint64_t* out /* [7] */) {
         out[6] = std::max<uint64_t>(out[6], (uint64_t)it.depth);
         int used = 0;
         for (uint32_t blk = 0; blk < kNodeWidth / 4; ++blk) {
-        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)it.node + kIndexBlockF4 * blk;
+        const float4* nd = S.inodes + kIndexNodeF4 * (size_t)(it.node & IREF_NODE_MASK) + kIndexBlockF4 * blk;
         const float4 q0 = nd[0], q1 = nd[1], q2 = nd[2], q3 = nd[3];
         float2 cx[2] = {unpack_half2(q0.x), unpack_half2(q0.y)}, cy[2] = {unpack_half2(q0.z), unpack_half2(q0.w)};
         float2 cz[2] = {unpack_half2(q1.x), unpack_half2(q1.y)}, hx[2] = {unpack_half2(q1.z), unpack_half2(q1.w)};

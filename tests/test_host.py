@@ -166,3 +166,34 @@ def test_parser_quirks_match_reference_golden(rtc):
         s.close()
         i += 1
     assert i == 4
+
+
+def test_bench_configs_and_reference_arm(tmp_path):
+    """bench.py: every BASELINE.json configuration resolves to its scene / size, and the reference arm prints the
+    contract's JSON line (a tiny sample here: 8x8 pixels, 1 spp of the 10k dragon through the compiled reference)."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    import orclib
+
+    class A:
+        scene = ""; width = -1; height = -1; spp = -1
+    want = {1: "practice5_1", 2: "practice5_dragon_10k", 3: "practice5_dragon_100k", 4: "practice5_dragon_100k_glass",
+            5: "practice5_dragon_100k_metal"}
+    for c, name in want.items():
+        a = A(); a.config = c
+        cfg = bench.resolve_config(a)
+        assert cfg["scene"] == name
+    a = A(); a.config = 5
+    assert (bench.resolve_config(a)["width"], bench.resolve_config(a)["height"], bench.resolve_config(a)["spp"]) == (3840, 2160, 1024)
+    if not orclib.have_ref():
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "2", "--steps", "1",
+                        "--warmup", "0", "--ref-width", "8", "--ref-height", "8", "--ref-spp", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "Mpaths/s" and line["value"] > 0
+    assert line["config"]["workload"] == "practice5_dragon_10k" and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True

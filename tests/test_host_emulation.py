@@ -296,7 +296,7 @@ def test_index_tree_is_pinned(emu):
     measurement (profiles/)."""
     emu.emu_index_hash.restype = C.c_uint64
     emu.emu_index_hash.argtypes = [C.c_void_p]
-    want = {"practice5_dragon_10k": 0x3489f252dd17952d, "practice5_dragon_100k": 0x8db8c0679a8cf812}
+    want = {"practice5_dragon_10k": 0x68b2830b139c73ad, "practice5_dragon_100k": 0x3c81806131a93e92}
     if os.environ.get("RTC_EMU_DEFS"):
         pytest.skip("pinned for the default build configuration")
     for name, value in want.items():

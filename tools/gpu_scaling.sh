@@ -1,25 +1,23 @@
 #!/bin/bash
-# tools/gpu_scaling.sh N [extra] -- on an N-GPU box: the headline workload at N ranks (the driver's own launch line);
-# with "extra" also BASELINE configs 3 (glass dragon) and 4 (metal dragon, 3840x2160, 1024 spp).
+# tools/gpu_scaling.sh -- on an 8-GPU box: the headline configuration at 8 / 4 ranks, BASELINE configurations 4 and 5 at 8
+# ranks, and the one-process multi-device call (rtc_render_u8_multi) on 1 / 2 / 4 / 8 devices
 cd "$(dirname "$0")/.."
-N=$1
 mkdir -p gpurun_out
-run() {  # name, bench args...
-  name=$1; shift
-  if [ "$N" = "1" ]; then timeout 600 python bench.py --gpus 1 "$@" > gpurun_out/scale_$name.log 2>&1
-  else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-         bench.py --gpus $N "$@" > gpurun_out/scale_$name.log 2>&1; fi
-  tail -1 gpurun_out/scale_$name.log | python -c '
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+summ() { tail -1 "$1" | python -c '
 import sys, json
 try:
-    d = json.loads(sys.stdin.read())
-    print("%-22s n=%d  Mpaths/s %.1f  Mrays/s %.1f  ms/step %.2f  e2e %.1f" % (sys.argv[1], d["n_gpus"], d["value"], d["mrays_per_s"], d["ms_per_step"], d["e2e"]["value"]))
+    d = json.loads(sys.stdin.read()); r = d["roofline"]
+    print("%-14s N=%d Mpaths/s %.1f  Mrays/s %.1f  ms/step %.2f  e2e %.1f (%.2f ms)  kernels %s" % (sys.argv[1], d["n_gpus"], d["value"], d["mrays_per_s"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], {k: round(v, 2) for k, v in r["kernel_ms_per_step"].items()}))
 except Exception as e:
-    print(sys.argv[1], "FAILED", e)' $name
+    print(sys.argv[1], "FAILED", e)' "$2"; }
+run() {  # name N extra-args
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $2 --warmup 3 ${@:3} > gpurun_out/bench_$1.log 2> gpurun_out/bench_$1.err || tail -8 gpurun_out/bench_$1.err
+  summ gpurun_out/bench_$1.log $1
 }
-run ${N}gpu --steps 10 --warmup 3 --no-cpu-baseline
-run ${N}gpu_pipeline --steps 10 --warmup 3 --no-cpu-baseline --pipeline
-if [ "$2" = "extra" ]; then
-  run config3_glass_${N}gpu --steps 10 --warmup 3 --no-cpu-baseline --scene practice5_dragon_100k_glass
-  run config4_metal_4k_1024spp_${N}gpu --steps 3 --warmup 3 --no-cpu-baseline --scene practice5_dragon_100k_metal --width 3840 --height 2160 --spp 1024
-fi
+run 8gpu 8 --steps 20
+run 4gpu 4 --steps 20
+run config4_glass_8gpu 8 --config 4 --steps 20
+run config5_metal_4k_8gpu 8 --config 5 --steps 3
+timeout 300 python tools/experiments/multi_probe.py 8 | tee gpurun_out/multi_probe_8.json
+timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "multi_device" 2>&1 | tail -2

@@ -159,7 +159,18 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // idle lanes REFILL from the queue.  Every iteration the warp votes and executes the kind most
 // lanes are ready for, which keeps lanes busy although rays need between one and several
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
+// RTC_SMEM_STACK=1 (experiment, off: measured slower): the traversal stack of a lane in shared memory, word w of thread t
+// at [w][t] -- conflict-free whatever the lanes' stack heights, where local memory pays one wavefront per distinct height
+#ifndef RTC_SMEM_STACK
+#define RTC_SMEM_STACK 0
+#endif
+#if RTC_SMEM_STACK
+constexpr int kStackWords = 32;  // 16 KB per block
+#define STK(i) sstk[(i) * 128 + threadIdx.x]
+#else
 constexpr int kStackWords = 56;  // per lane: inner-node stack from the bottom, noted leaves from the top
+#define STK(i) stk[i]
+#endif
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 #ifndef RTC_LEAF_FIRST
 #define RTC_LEAF_FIRST 8
@@ -189,7 +200,11 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
     ConeDir dn{0u, 0u};
     float cd0 = 0.f;
     int sp = 0, nl = 0, k = 0;
+#if RTC_SMEM_STACK
+    __shared__ uint32_t sstk[kStackWords * 128];
+#else
     uint32_t stk[kStackWords];
+#endif
     LeafRec rec[kMaxRecords];
     uint32_t visits = 0, tests = 0, fallbacks = 0;
     uint32_t iters[4] = {0, 0, 0, 0}, busy[4] = {0, 0, 0, 0};  // STATS: warp iterations and participating lanes per kind
@@ -243,17 +258,17 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 if (STATS) ++visits;
                 NodeVisit v = index_visit(S, node, inv, oi, dn);
                 const int spm = sp > 0 ? sp - 1 : 0;
-                const uint32_t top = stk[spm];
+                const uint32_t top = STK(spm);
                 uint32_t next = kNone;
 #pragma unroll
                 for (int c = 0; c < (int)kNodeWidth; ++c) {
                     const bool leaf = (v.ref[c] & IREF_LEAF) != 0;
                     if (v.hit[c] && leaf) {  // note the leaf, test it later
                         ++nl;
-                        stk[kStackWords - nl] = v.ref[c];
+                        STK(kStackWords - nl) = v.ref[c];
                     }
                     const bool inner = v.hit[c] && !leaf;
-                    if (inner && next != kNone) { stk[sp] = v.ref[c]; ++sp; }
+                    if (inner && next != kNone) { STK(sp) = v.ref[c]; ++sp; }
                     next = (inner && next == kNone) ? v.ref[c] : next;
                 }
                 const bool pop = next == kNone && sp > 0;
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
         } else if (kind == kLeaf) {
             // ---- LEAF: one noted reference leaf per ready lane
             if (canL) {
-                const uint32_t ref = stk[kStackWords - nl];
+                const uint32_t ref = STK(kStackWords - nl);
                 --nl;
                 float bt, tc; int bid;
                 if (leaf_test(S, ref, o, d, inv, oi, bt, bid, tc, STATS ? &tests : nullptr) && bid >= 0) {
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 node = kNone;
                 if (S.iroot & IREF_LEAF) {  // single-leaf tree
                     nl = 1;
-                    stk[kStackWords - 1] = S.iroot;
+                    STK(kStackWords - 1) = S.iroot;
                 } else {
                     // the root was visited when the ray was made (pre_step): start from the children it entered.
                     // (Measured on B200: 6.56 instead of 7.56 visits per ray and the same 11.65 ms -- the root visit of
@@ -315,9 +330,9 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t ref = S.iroot_ref[c];
                         if (!((entry >> (kTqSlotBits + c)) & 1u)) continue;
-                        if (ref & IREF_LEAF) { ++nl; stk[kStackWords - nl] = ref; }
+                        if (ref & IREF_LEAF) { ++nl; STK(kStackWords - nl) = ref; }
                         else if (node == kNone) node = ref;
-                        else { stk[sp] = ref; ++sp; }
+                        else { STK(sp) = ref; ++sp; }
                     }
                 }
             }
@@ -377,7 +392,7 @@ RT_D void deposit(float4* accum4, uint32_t pixel, vec3 L) {
 #define RTC_SHADE_MIN_BLOCKS_FULL 6
 #endif
 #ifndef RTC_SHADE_MIN_BLOCKS_LEAN
-#define RTC_SHADE_MIN_BLOCKS_LEAN 8
+#define RTC_SHADE_MIN_BLOCKS_LEAN 9   // round 2 (52-byte state, two-ended queues): 7 / 8 / 9 blocks: 7.17 / 6.74 / 6.62 ms
 #endif
 // HW3 = the hw3 snapshot's diffuse term (hw3 src/scene.cpp:238-249): a direction uniform on the hemisphere
 // around the normal, weight 2 C cos; every other line of the switch is common to hw3, hw4 and hw5.

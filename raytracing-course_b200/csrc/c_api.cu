@@ -134,6 +134,8 @@ struct rtc_scene {
     static constexpr int kMaxLanes = 4;
     Lane lanes[kMaxLanes];
     int nlanes = 2;                      // env RTC_STREAMS (1..4)
+    unsigned next_lane = 0;              // small renders take the lanes in turn
+    uint64_t small_render_paths = 0;     // env RTC_SMALL_RENDER (paths): renders up to this size are one batch on one lane
     cudaEvent_t fork = nullptr;
     DevBuf<unsigned long long> stats;    // 16 words: rtc_render_counters (8) + rtc_traverse_lanes (8)
     DevBuf<float> accum;                 // internal accumulation buffer for the convenience calls
@@ -325,6 +327,7 @@ int finish_scene(rtc_scene* s, int device) {
         int n = std::atoi(v);
         s->nlanes = n < 1 ? 1 : (n > rtc_scene::kMaxLanes ? rtc_scene::kMaxLanes : n);
     }
+    if (const char* v = std::getenv("RTC_SMALL_RENDER")) s->small_render_paths = std::strtoull(v, nullptr, 10);
     s->device = device;
     if (device >= 0) {
         int count = 0;
@@ -704,13 +707,18 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     // batch size: the configured one, but small enough that every lane gets a batch (overlap matters
     // more than batch size: profiles/r01_experiments.md), rounded up to whole warps
     uint64_t cap = total < s->batch_paths ? total : s->batch_paths;
-    if (!s->profiling && s->nlanes > 1) {
+    // A small render (the share of one GPU of eight: 4 Mi paths) is ONE batch on the next lane in turn instead of one
+    // batch per lane: its launches are twice as large (a persistent k_traverse launch ends with its longest ray, ~30 us
+    // whatever its size), and the overlap comes from the caller's next render, which takes the other lane.
+    const bool whole = !s->profiling && s->nlanes > 1 && total <= s->small_render_paths;
+    if (!s->profiling && s->nlanes > 1 && !whole) {
         uint64_t per_lane = ((total + s->nlanes - 1) / s->nlanes + 31) & ~(uint64_t)31;
         if (per_lane < cap) cap = per_lane;
     }
     const uint64_t nbatches = (total + cap - 1) / cap;
     // per-kernel event timing needs the kernels back to back on one stream
-    const int nlanes = s->profiling ? 1 : (int)(nbatches < (uint64_t)s->nlanes ? nbatches : (uint64_t)s->nlanes);
+    const int nlanes = s->profiling ? 1 : whole ? s->nlanes : (int)(nbatches < (uint64_t)s->nlanes ? nbatches : (uint64_t)s->nlanes);
+    const int lane_first = whole ? (int)(s->next_lane++ % (unsigned)s->nlanes) : 0;
     if ((rc = ensure_wavefront(s, cap, nlanes))) return rc;
     cudaStream_t user = (cudaStream_t)stream;
     // the float4 pixel sums of this render: two buffers used alternately, so that two renders may be in flight on
@@ -727,10 +735,11 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     DevScene S = s->dev();
     // fork: the lane streams start after everything already queued on the caller's stream
     CU(cudaEventRecord(s->fork, user));
-    for (int i = 0; i < nlanes; ++i) CU(cudaStreamWaitEvent(s->lanes[i].stream, s->fork, 0));
+    for (int i = 0; i < nlanes; ++i)
+        if (!whole || i == lane_first) CU(cudaStreamWaitEvent(s->lanes[i].stream, s->fork, 0));
     uint64_t batch = 0;
     for (uint64_t first = 0; first < total; first += cap, ++batch) {
-        rtc_scene::Lane& L = s->lanes[batch % nlanes];
+        rtc_scene::Lane& L = s->lanes[(lane_first + batch) % nlanes];
         cudaStream_t st = L.stream;
         LaunchCtx c{st, s->sms};
         uint32_t* tqc = L.queue.p + 2 * kMaxDepthSlots;    // rays queued for k_traverse, per bounce
@@ -762,6 +771,7 @@ int rtc_render_accumulate(rtc_scene* s, uint32_t seed, uint32_t sample_begin, ui
     }
     // join: the caller's stream continues when every lane is done
     for (int i = 0; i < nlanes; ++i) {
+        if (whole && i != lane_first) continue;   // the other lanes belong to the caller's other renders
         CU(cudaEventRecord(s->lanes[i].done, s->lanes[i].stream));
         CU(cudaStreamWaitEvent(user, s->lanes[i].done, 0));
     }

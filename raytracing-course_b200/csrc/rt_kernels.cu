@@ -156,11 +156,17 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // Persistent warps with a per-warp task scheduler.  The traversal reports ALL touched leaves in
 // any order, so the three kinds of work of a ray are decoupled: VISIT one inner node (children
 // that are leaves are only noted down), test one noted LEAF, FINISH the ray (replay + store);
-// idle lanes REFILL from the queue.  Every iteration the warp votes and executes the kind most
+// idle lanes REFILL from the queue (FINISH and REFILL share an iteration: a lane that stores its result takes its
+// next ray at once).  Every iteration the warp votes and executes the kind most
 // lanes are ready for, which keeps lanes busy although rays need between one and several
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
 // RTC_SMEM_STACK=1 (experiment, off: measured slower): the traversal stack of a lane in shared memory, word w of thread t
 // at [w][t] -- conflict-free whatever the lanes' stack heights, where local memory pays one wavefront per distinct height
+// FINISH and REFILL as one kind of scheduler work: measured on B200 11.52 -> 10.90 ms (the two used to cost a vote and a
+// partly filled warp iteration each: 5.3 M + 5.4 M iterations per frame at 15.7 / 17.7 lanes)
+#ifndef RTC_FUSE_RETIRE
+#define RTC_FUSE_RETIRE 1
+#endif
 #ifndef RTC_SMEM_STACK
 #define RTC_SMEM_STACK 0
 #endif
@@ -238,12 +244,22 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             nR = __popc(mR);
             // lanes holding noted leaves are served before the plain majority vote once there are enough
             // of them (threshold swept on B200: profiles/r01_experiments.md)
+#if RTC_FUSE_RETIRE
+            // FINISH and REFILL are one kind of work: a lane whose ray is done stores its result and takes the next ray in
+            // the same iteration (kind kFinish stands for both)
+            const int nT = __popc(mF | mR);
+            if (nL >= RTC_LEAF_FIRST) kind = kLeaf;
+            else if (nV >= nL && nV >= nT) kind = kVisit;
+            else if (nL >= nT) kind = kLeaf;
+            else kind = kFinish;
+#else
             if (nL >= RTC_LEAF_FIRST) kind = kLeaf;
             else
             if (nV >= nL && nV >= nF && nV >= nR) kind = kVisit;
             else if (nL >= nF && nL >= nR) kind = kLeaf;
             else if (nF >= nR) kind = kFinish;
             else kind = kRefill;
+#endif
         }
 
         if (STATS) {  // warp-execution efficiency of the scheduler: lanes that take part in this iteration
@@ -286,7 +302,8 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                     else { rec[k].key = ref & 0xFFFFFFu; rec[k].id = bid; rec[k].t = bt; rec[k].tcull = tc; ++k; }
                 }
             }
-        } else if (kind == kFinish) {
+        } else {
+          if (kind == kFinish) {
             // ---- FINISH: replay of the reference recursion, store the winner
             if (canF) {
                 BestHit b;
@@ -295,7 +312,14 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 if (b.id != -1 && b.t < cd0) WF_ST(H.id + ray, (uint32_t)b.id);  // src/scene.cpp:68-74
                 active = false;
             }
-        } else {
+#if RTC_FUSE_RETIRE
+            canR = !active && (pool_left > 0 || !exhausted);
+            mR = __ballot_sync(kFullMask, canR);
+            nR = __popc(mR);
+            if (STATS) { iters[kRefill] += 1; busy[kRefill] += (uint32_t)nR; }
+#endif
+          }
+          if (kind == kRefill || RTC_FUSE_RETIRE) {
             // ---- REFILL idle lanes from the queue
             if (pool_left == 0) {
                 uint32_t base = 0;
@@ -338,6 +362,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             }
             pool_base += serve;
             pool_left -= serve;
+          }
         }
     }
     if (fallbacks) atomicAdd(stats + 5, (unsigned long long)fallbacks);

@@ -340,14 +340,21 @@ def main():
             while pending:
                 scene.frame_end(pending.pop(0))
         else:
+            cur = torch.cuda.current_stream()
+            for st in streams:
+                st.wait_stream(cur)
             for i in range(nsteps):
-                accum = accums[0]
+                accum, st = accums[i & 1], streams[i & 1]   # two frames in flight on alternating streams, as above
                 h2d = scene.upload_async()
-                accum.zero_()
-                scene.render_accumulate(accum.data_ptr(), seed=2000 + first_step + i, sample_begin=lo, sample_count=hi - lo)
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    scene.resolve_to_host(accum.data_ptr(), spp)
+                with torch.cuda.stream(st):
+                    accum.zero_()
+                    scene.render_accumulate(accum.data_ptr(), seed=2000 + first_step + i, sample_begin=lo, sample_count=hi - lo,
+                                            stream=st.cuda_stream)
+                    dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+                    if rank == 0:
+                        scene.resolve_to_host(accum.data_ptr(), spp, stream=st.cuda_stream)
+            for st in streams:
+                cur.wait_stream(st)
             if rank == 0:
                 scene.host_image_wait()
         barrier()
@@ -418,7 +425,7 @@ def main():
                 "mrays_per_s": mrays, "rays_per_path": total_rays / max(total_paths, 1),
                 "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": int(npix * 3), "ms_per_step": e2e_ms / args.steps,
-                        "frames_in_flight": 2 if world == 1 else 1},
+                        "frames_in_flight": 2},
                 "load_s": load_s, "cli_s": cli_s,
                 "gpu_launches": int(total_launches), "fallback_rays": cnt["fallback_rays"],
                 "clocks": clocks, "roofline": rooflines[top], "rooflines": rooflines, "peaks": peaks, "cpu_baseline": cpu}

@@ -137,7 +137,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.01)
 
     def result(self):
         self.stop_flag.set()
@@ -396,10 +396,10 @@ def main():
     e2e_ms, h2d_bytes = timed_e2e(args.steps, 200)
 
     paths_rank = npix * (hi - lo) * args.steps
-    t_paths = torch.tensor([float(paths_rank), float(cnt["rays"]), float(cnt["launches"])], dtype=torch.float64, device=dev)
+    t_paths = torch.tensor([float(paths_rank), float(cnt["rays"]), float(cnt["launches"]), float(h2d_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_paths, op=dist.ReduceOp.SUM)
-    total_paths, total_rays, total_launches = [float(x) for x in t_paths.tolist()]
+    total_paths, total_rays, total_launches, h2d_bytes = [float(x) for x in t_paths.tolist()]   # whole job: every rank uploads its scene
     ms_per_step = ms_total / args.steps
     value = total_paths / (ms_total * 1e-3) / 1e6
     mrays = total_rays / (ms_total * 1e-3) / 1e6

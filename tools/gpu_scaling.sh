@@ -17,6 +17,7 @@ run() {  # name N extra-args
 }
 run 8gpu 8 --steps 20
 run 4gpu 4 --steps 20
+run 2gpu 2 --steps 20
 run config4_glass_8gpu 8 --config 4 --steps 20
 run config5_metal_4k_8gpu 8 --config 5 --steps 3
 timeout 300 python tools/experiments/multi_probe.py 8 | tee gpurun_out/multi_probe_8.json

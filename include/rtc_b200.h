@@ -64,6 +64,10 @@ int rtc_scene_upload(rtc_scene* s, uint64_t* h2d_bytes);
 
 /* out: width,height,ray_depth,samples,nprims,nbvh(non-plane prims),nnodes(reference BVH),nlights */
 int rtc_scene_info(const rtc_scene* s, uint32_t out[8]);
+/* Only the head of the flattened scene travels to the device (rtc_scene_upload*); its tail -- the upper levels of the
+ * LCA table, the per-slot exact leaf boxes, identity rotations -- is rebuilt there.  Compares the arena in HBM, byte for
+ * byte, with the one the host would have uploaded in full (tests). */
+int rtc_scene_arena_check(rtc_scene* s, uint64_t* mismatching_bytes);
 /* out: index-BVH nodes, index-BVH depth, reference-BVH depth, units(reference leaves),
  *      device bytes of the scene, LCA table levels, bytes per index node, scene feature bits */
 int rtc_scene_stats(const rtc_scene* s, uint64_t out[8]);

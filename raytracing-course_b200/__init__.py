@@ -58,6 +58,7 @@ _SIGNATURES = {
     "rtc_render_counters": (C.c_int, [C.c_void_p, C.c_void_p, _u64]),
     "rtc_render_reset_counters": (C.c_int, [C.c_void_p]),
     "rtc_traverse_lanes": (C.c_int, [C.c_void_p, C.c_void_p, _u64]),
+    "rtc_scene_arena_check": (C.c_int, [C.c_void_p, _u64]),
     "rtc_intersect_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int, C.c_void_p]),
     "rtc_render_u8_multi": (C.c_int, [C.c_void_p, _i32, C.c_int, C.c_uint32, _u8, C.c_void_p]),
@@ -303,6 +304,12 @@ class Scene:
         _check(self.lib, self.lib.rtc_render_u8_multi(self.h, dv, len(dv), seed, out,
                                                       total.ctypes.data_as(C.c_void_p) if want_sum else None))
         return (out, total) if want_sum else out
+
+    def arena_check(self):
+        """Bytes of the scene arena in HBM that differ from the arena the host would have uploaded in full."""
+        n = np.zeros(1, np.uint64)
+        _check(self.lib, self.lib.rtc_scene_arena_check(self.h, n))
+        return int(n[0])
 
     def upload_async(self):
         """Queue the H2D copy of the flattened scene into the arena that is not being read; the next render waits for it."""

@@ -79,7 +79,15 @@ struct rtc_scene {
     unsigned char* arena_dev[2] = {nullptr, nullptr};
     unsigned char* arena_host = nullptr;  // cudaMallocHost
     size_t arena_bytes = 0;
-    size_t part_off[16] = {0};            // offsets of the scene arrays inside an arena
+    size_t part_off[16] = {0};            // offsets of the scene arrays inside an arena (index = ArenaPart)
+    // Only the head of an arena travels over the host link; its tail -- levels >= 1 of the LCA range-minimum table,
+    // the exact boxes of the few leaves that need them, the identity rotations of a scene without rotated
+    // primitives: 11 of 35 MB for the 100k dragon -- is a pure function of the head and is rebuilt on the device
+    // after every upload (expand_arena), on the copy stream, under the kernels of the previous frame.
+    size_t upload_bytes = 0;              // size of the head = bytes per H2D copy (and of the pinned mirror)
+    size_t sparse_boxes = 0;              // entries of the part ubox_sparse: (slot, min, max) of the leaves with an explicit box
+    bool rot_generated = false;           // xf_rot is all identity and lives in the tail
+    std::vector<unsigned char> arena_full; // the whole arena as the host would have uploaded it (tests: rtc_scene_arena_check)
     int arena_cur = 0;                    // the arena the next render reads
     DevScene slices{};                    // pointers into arena_dev[arena_cur] (scalars filled by dev())
     cudaStream_t copy_stream = nullptr;
@@ -236,21 +244,23 @@ struct rtc_scene {
 
 namespace {
 
-// Lays the flat scene arrays out in one arena (256-byte aligned slices).  First call: allocates the device arena
-// and its pinned host mirror and fills the mirror.
+// Lays the flat scene arrays out in one arena (256-byte aligned slices): first everything that has to be uploaded, then
+// what the device derives from it.
+enum ArenaPart { A_GEO0, A_GEO1, A_GEO2, A_XF_POS, A_MAT0, A_MAT1, A_INODES, A_RNODES, A_RMETA, A_LIGHTS, A_PLANES, A_PLIGHTS,
+                 A_UBOX_SPARSE, A_XF_ROT, A_LCA, A_UBOX, A_COUNT };
 void point_slices(rtc_scene* s, int which) {
     unsigned char* base = s->arena_dev[which];
     const size_t* off = s->part_off;
     DevScene& D = s->slices;
-    D.geo0 = (const float4*)(base + off[0]);   D.geo1 = (const float4*)(base + off[1]);
-    D.geo2 = (const float4*)(base + off[2]);   D.xf_pos = (const float4*)(base + off[3]);
-    D.xf_rot = (const float4*)(base + off[4]); D.mat0 = (const float4*)(base + off[5]);
-    D.mat1 = (const float4*)(base + off[6]);   D.inodes = (const float4*)(base + off[7]);
-    D.rnodes = (const float4*)(base + off[8]); D.rmeta = (const uint4*)(base + off[9]);
-    D.lca = (const uint32_t*)(base + off[10]); D.lights = (const int32_t*)(base + off[11]);
-    D.planes = (const float4*)(base + off[12]);
-    D.ubox = (const float4*)(base + off[13]);
-    D.plights = (const float4*)(base + off[14]);
+    D.geo0 = (const float4*)(base + off[A_GEO0]);     D.geo1 = (const float4*)(base + off[A_GEO1]);
+    D.geo2 = (const float4*)(base + off[A_GEO2]);     D.xf_pos = (const float4*)(base + off[A_XF_POS]);
+    D.xf_rot = (const float4*)(base + off[A_XF_ROT]); D.mat0 = (const float4*)(base + off[A_MAT0]);
+    D.mat1 = (const float4*)(base + off[A_MAT1]);     D.inodes = (const float4*)(base + off[A_INODES]);
+    D.rnodes = (const float4*)(base + off[A_RNODES]); D.rmeta = (const uint4*)(base + off[A_RMETA]);
+    D.lca = (const uint32_t*)(base + off[A_LCA]);     D.lights = (const int32_t*)(base + off[A_LIGHTS]);
+    D.planes = (const float4*)(base + off[A_PLANES]);
+    D.ubox = (const float4*)(base + off[A_UBOX]);
+    D.plights = (const float4*)(base + off[A_PLIGHTS]);
     s->arena_cur = which;
 }
 int prepare_arena(rtc_scene* s) {
@@ -258,35 +268,56 @@ int prepare_arena(rtc_scene* s) {
     CU(cudaSetDevice(s->device));
     if (s->arena_host) return RTC_OK;
     const FlatScene& F = s->host.flat;
+    // the leaves whose exact box cannot be read off a single untransformed triangle: (slot, min, max) = 3 float4 each
+    std::vector<f4> sparse;
+    for (size_t i = 0; 2 * i + 1 < F.ubox.size(); ++i) {
+        const f4 &mn = F.ubox[2 * i], &mx = F.ubox[2 * i + 1];
+        const bool zero = mn.x == 0.f && mn.y == 0.f && mn.z == 0.f && mn.w == 0.f && mx.x == 0.f && mx.y == 0.f && mx.z == 0.f && mx.w == 0.f
+                          && !std::signbit(mn.x) && !std::signbit(mn.y) && !std::signbit(mn.z) && !std::signbit(mx.x) && !std::signbit(mx.y) && !std::signbit(mx.z);
+        if (zero) continue;
+        f4 slot{0.f, 0.f, 0.f, 0.f};
+        const uint32_t idx = (uint32_t)i;
+        std::memcpy(&slot.x, &idx, 4);
+        sparse.push_back(slot); sparse.push_back(mn); sparse.push_back(mx);
+    }
+    s->sparse_boxes = sparse.size() / 3;
+    s->rot_generated = !(F.features & FE_ROTATION);   // every rotation is (0, 0, 0, 1)
+    for (const f4& q : F.xf_rot)
+        if (!(q.x == 0.f && q.y == 0.f && q.z == 0.f && q.w == 1.f) || std::signbit(q.x) || std::signbit(q.y) || std::signbit(q.z)) s->rot_generated = false;
     struct Part { const void* src; size_t bytes; };
-    const Part parts[] = {
-        {F.geo0.data(), F.geo0.size() * sizeof(f4)},     {F.geo1.data(), F.geo1.size() * sizeof(f4)},
-        {F.geo2.data(), F.geo2.size() * sizeof(f4)},     {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4)},
-        {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4)}, {F.mat0.data(), F.mat0.size() * sizeof(f4)},
-        {F.mat1.data(), F.mat1.size() * sizeof(f4)},     {F.inodes.data(), F.inodes.size() * sizeof(f4)},
-        {F.rnodes.data(), F.rnodes.size() * sizeof(f4)}, {F.rmeta.data(), F.rmeta.size() * sizeof(u4)},
-        {F.lca.data(), F.lca.size() * sizeof(uint32_t)}, {F.lights.data(), F.lights.size() * sizeof(int32_t)},
-        {F.planes.data(), F.planes.size() * sizeof(f4)}, {F.ubox.data(), F.ubox.size() * sizeof(f4)},
-        {F.plights.data(), F.plights.size() * sizeof(f4)},
-    };
-    size_t total = 0, payload = 0;
-    int i = 0;
-    for (const Part& p : parts) {
-        s->part_off[i++] = total;
-        total += (p.bytes + 255) & ~(size_t)255;
-        payload += p.bytes;
+    Part parts[A_COUNT];
+    parts[A_GEO0] = {F.geo0.data(), F.geo0.size() * sizeof(f4)};       parts[A_GEO1] = {F.geo1.data(), F.geo1.size() * sizeof(f4)};
+    parts[A_GEO2] = {F.geo2.data(), F.geo2.size() * sizeof(f4)};       parts[A_XF_POS] = {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4)};
+    parts[A_MAT0] = {F.mat0.data(), F.mat0.size() * sizeof(f4)};       parts[A_MAT1] = {F.mat1.data(), F.mat1.size() * sizeof(f4)};
+    parts[A_INODES] = {F.inodes.data(), F.inodes.size() * sizeof(f4)}; parts[A_RNODES] = {F.rnodes.data(), F.rnodes.size() * sizeof(f4)};
+    parts[A_RMETA] = {F.rmeta.data(), F.rmeta.size() * sizeof(u4)};    parts[A_LIGHTS] = {F.lights.data(), F.lights.size() * sizeof(int32_t)};
+    parts[A_PLANES] = {F.planes.data(), F.planes.size() * sizeof(f4)}; parts[A_PLIGHTS] = {F.plights.data(), F.plights.size() * sizeof(f4)};
+    parts[A_UBOX_SPARSE] = {sparse.data(), sparse.size() * sizeof(f4)};
+    parts[A_XF_ROT] = {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4)};
+    parts[A_LCA] = {F.lca.data(), F.lca.size() * sizeof(uint32_t)};
+    parts[A_UBOX] = {F.ubox.data(), F.ubox.size() * sizeof(f4)};
+    size_t total = 0, head = 0;
+    for (int i = 0; i < A_COUNT; ++i) {
+        s->part_off[i] = total;
+        total += (parts[i].bytes + 255) & ~(size_t)255;
+        // the head ends before the rotations when they are all identity, behind them otherwise; level 0 of the LCA table
+        // (the only level that travels) is a second, small copy
+        if (i < A_XF_ROT || (i == A_XF_ROT && !s->rot_generated)) head = total;
     }
     if (total == 0) total = 256;
-    CU(cudaMalloc(&s->arena_dev[0], total));
-    CU(cudaMallocHost(&s->arena_host, total));
-    std::memset(s->arena_host, 0, total);
-    i = 0;
-    for (const Part& p : parts) {
-        if (p.bytes) std::memcpy(s->arena_host + s->part_off[i], p.src, p.bytes);
-        ++i;
-    }
+    s->arena_full.assign(total, 0);
+    for (int i = 0; i < A_COUNT; ++i)
+        if (parts[i].bytes) std::memcpy(s->arena_full.data() + s->part_off[i], parts[i].src, parts[i].bytes);
+    s->upload_bytes = head;
     s->arena_bytes = total;
-    s->device_bytes = payload;
+    CU(cudaMalloc(&s->arena_dev[0], total));
+    CU(cudaMemset(s->arena_dev[0], 0, total));   // the padding between the device-built parts is never written again
+    // pinned mirror of what travels: the head, and level 0 of the LCA table right behind it
+    const size_t level0 = F.lca_levels ? (((size_t)s->host.nbvh * sizeof(uint32_t) + 255) & ~(size_t)255) : 0;
+    CU(cudaMallocHost(&s->arena_host, head + level0 + 256));
+    std::memcpy(s->arena_host, s->arena_full.data(), head);
+    if (level0) std::memcpy(s->arena_host + head, s->arena_full.data() + s->part_off[A_LCA], (size_t)s->host.nbvh * sizeof(uint32_t));
+    s->device_bytes = head + (F.lca_levels ? (size_t)s->host.nbvh * sizeof(uint32_t) : 0);
     point_slices(s, 0);
     for (int a = 0; a < 2; ++a) {
         CU(cudaEventCreateWithFlags(&s->arena_ready[a], cudaEventDisableTiming));
@@ -298,12 +329,32 @@ int prepare_arena(rtc_scene* s) {
     CU(cudaMemset(s->stats.p, 0, kStatWords * sizeof(unsigned long long)));
     return RTC_OK;
 }
-// synchronous upload into the arena in use: ONE H2D copy, complete on return
+// H2D copies of the head (+ LCA level 0) into arena `target`, then the device-side rebuild of the tail; all on `st`
+int issue_upload(rtc_scene* s, int target, cudaStream_t st) {
+    unsigned char* dev = s->arena_dev[target];
+    const FlatScene& F = s->host.flat;
+    if (s->upload_bytes) CU(cudaMemcpyAsync(dev, s->arena_host, s->upload_bytes, cudaMemcpyHostToDevice, st));
+    const size_t level0 = F.lca_levels ? (size_t)s->host.nbvh * sizeof(uint32_t) : 0;
+    if (level0) CU(cudaMemcpyAsync(dev + s->part_off[A_LCA], s->arena_host + s->upload_bytes, level0, cudaMemcpyHostToDevice, st));
+    LaunchCtx c{st, s->sms};
+    if (F.lca_levels > 1)
+        launch_expand_lca(c, (uint32_t*)(dev + s->part_off[A_LCA]), (const uint4*)(dev + s->part_off[A_RMETA]), s->host.nbvh, F.lca_levels);
+    if (!F.ubox.empty()) {
+        CU(cudaMemsetAsync(dev + s->part_off[A_UBOX], 0, F.ubox.size() * sizeof(f4), st));
+        if (s->sparse_boxes)
+            launch_expand_boxes(c, (const float4*)(dev + s->part_off[A_UBOX_SPARSE]), (uint32_t)s->sparse_boxes, (float4*)(dev + s->part_off[A_UBOX]));
+    }
+    if (s->rot_generated && !F.xf_rot.empty())
+        launch_fill_identity_rotations(c, (float4*)(dev + s->part_off[A_XF_ROT]), (uint32_t)F.xf_rot.size());
+    CU(cudaGetLastError());
+    return RTC_OK;
+}
+// synchronous upload into the arena in use, complete on return
 int upload_scene(rtc_scene* s, uint64_t* h2d) {
     int rc = prepare_arena(s);
     if (rc) return rc;
     CU(cudaDeviceSynchronize());   // nothing may still be reading the arena
-    CU(cudaMemcpyAsync(s->arena_dev[s->arena_cur], s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, s->copy_stream));
+    if ((rc = issue_upload(s, s->arena_cur, s->copy_stream))) return rc;
     CU(cudaStreamSynchronize(s->copy_stream));
     s->arena_pending = false;
     if (h2d) *h2d = s->device_bytes;
@@ -314,9 +365,12 @@ int upload_scene_async(rtc_scene* s, uint64_t* h2d) {
     int rc = prepare_arena(s);
     if (rc) return rc;
     const int target = 1 - s->arena_cur;
-    if (!s->arena_dev[target]) CU(cudaMalloc(&s->arena_dev[target], s->arena_bytes));
+    if (!s->arena_dev[target]) {
+        CU(cudaMalloc(&s->arena_dev[target], s->arena_bytes));
+        CU(cudaMemsetAsync(s->arena_dev[target], 0, s->arena_bytes, s->copy_stream));
+    }
     CU(cudaStreamWaitEvent(s->copy_stream, s->arena_idle[target], 0));   // the renders that read it are done
-    CU(cudaMemcpyAsync(s->arena_dev[target], s->arena_host, s->arena_bytes, cudaMemcpyHostToDevice, s->copy_stream));
+    if ((rc = issue_upload(s, target, s->copy_stream))) return rc;
     CU(cudaEventRecord(s->arena_ready[target], s->copy_stream));
     point_slices(s, target);
     s->arena_pending = true;
@@ -475,6 +529,18 @@ int rtc_scene_upload(rtc_scene* s, uint64_t* h2d_bytes) {
     int rc = need_device(s);
     if (rc) return rc;
     return upload_scene(s, h2d_bytes);
+}
+int rtc_scene_arena_check(rtc_scene* s, uint64_t* mismatching_bytes) {
+    int rc = need_device(s);
+    if (rc) return rc;
+    if (!mismatching_bytes) return fail(RTC_ERR_ARG, "null argument");
+    CU(cudaDeviceSynchronize());
+    std::vector<unsigned char> got(s->arena_bytes);
+    CU(cudaMemcpy(got.data(), s->arena_dev[s->arena_cur], s->arena_bytes, cudaMemcpyDeviceToHost));
+    uint64_t bad = 0;
+    for (size_t i = 0; i < s->arena_bytes; ++i) bad += got[i] != s->arena_full[i];
+    *mismatching_bytes = bad;
+    return RTC_OK;
 }
 int rtc_scene_info(const rtc_scene* s, uint32_t out[8]) {
     if (!s || !out) return fail(RTC_ERR_ARG, "null argument");

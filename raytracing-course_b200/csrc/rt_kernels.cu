@@ -615,6 +615,28 @@ __global__ void __launch_bounds__(256) k_tonemap(const float* rgb, uint32_t nval
         out[i] = to_u8(aces(rgb[i]));
 }
 
+// ------------------------------------------------------------------------------- scene arena, device-built tail
+// Levels >= 1 of the LCA range-minimum table (bvh_build.cpp: lca[l][c] = the shallower of lca[l-1][c] and
+// lca[l-1][c + 2^(l-1)]) from level 0, which is uploaded; one launch per level.
+__global__ void __launch_bounds__(256) k_expand_lca_level(const uint32_t* prev, uint32_t* cur, const uint4* rmeta, uint32_t n, uint32_t half) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const uint32_t a = prev[c], b = (c + half < n) ? prev[c + half] : 0xFFFFFFFFu;
+        const uint32_t da = a == 0xFFFFFFFFu ? 0xFFFFFFFFu : rmeta[a].z, db = b == 0xFFFFFFFFu ? 0xFFFFFFFFu : rmeta[b].z;
+        cur[c] = db < da ? b : a;
+    }
+}
+// exact boxes of the leaves that have one: (slot, min, max) triples scattered into the (zeroed) per-slot array
+__global__ void __launch_bounds__(256) k_expand_boxes(const float4* sparse, uint32_t n, float4* ubox) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = __float_as_uint(sparse[3 * i].x);
+        ubox[2 * (size_t)slot] = sparse[3 * i + 1];
+        ubox[2 * (size_t)slot + 1] = sparse[3 * i + 2];
+    }
+}
+__global__ void __launch_bounds__(256) k_fill_identity_rotations(float4* rot, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) rot[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+
 // ------------------------------------------------------------------------------- probes
 // rtc_intersect: rays given as 3 floats each -> the float4 queue layout of the render path, and
 // back from primitive ids to (t, normal, interior) by re-intersecting the winner.
@@ -728,6 +750,16 @@ void launch_shade(const LaunchCtx& c, const DevScene& S, PathSoA P, HitSoA H, Pa
     else if (feat == FE_SPECULAR) RTC_SHADE(false, FE_SPECULAR);
     else RTC_SHADE(false, FE_ALL);
 #undef RTC_SHADE
+}
+void launch_expand_lca(const LaunchCtx& c, uint32_t* lca, const uint4* rmeta, uint32_t n, uint32_t levels) {
+    for (uint32_t l = 1; l < levels; ++l)
+        k_expand_lca_level<<<grid_for(n, 256, c.sms, 8), 256, 0, c.stream>>>(lca + (size_t)(l - 1) * n, lca + (size_t)l * n, rmeta, n, 1u << (l - 1));
+}
+void launch_expand_boxes(const LaunchCtx& c, const float4* sparse, uint32_t n, float4* ubox) {
+    k_expand_boxes<<<grid_for(n, 256, c.sms, 8), 256, 0, c.stream>>>(sparse, n, ubox);
+}
+void launch_fill_identity_rotations(const LaunchCtx& c, float4* rot, uint32_t n) {
+    k_fill_identity_rotations<<<grid_for(n, 256, c.sms, 8), 256, 0, c.stream>>>(rot, n);
 }
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats) {
     k_tally<<<1, 1, 0, c.stream>>>(q, tqc, ray_depth, stats);

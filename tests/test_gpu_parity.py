@@ -484,3 +484,23 @@ def test_intersect_on_device_arrays(rtc, gpu_scenes):
     assert np.array_equal(tid.cpu().numpy(), pid)
     assert np.array_equal(tt.cpu().numpy(), t)
     assert np.array_equal(ti.cpu().numpy(), inter)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["practice5_1", "lights_mix", "rabbid", "practice5_dragon_10k", "practice5_dragon_100k"])
+def test_device_built_arena_tail_is_byte_identical(rtc, name):
+    """Only the head of the flattened scene is uploaded; the upper levels of the LCA table, the per-slot leaf boxes and
+    (for scenes without rotated primitives) the identity rotations are rebuilt on the device.  The arena in HBM must be,
+    byte for byte, the one the host would have uploaded in full -- after the load, after a synchronous re-upload and
+    after asynchronous uploads into both arenas."""
+    s = rtc.Scene(path=scene_path(name), device=0)
+    assert s.arena_check() == 0
+    full = s.stats()["device_bytes"]
+    assert s.upload() == full
+    assert s.arena_check() == 0
+    s.override(32, 32, 1)
+    for _ in range(2):
+        s.upload_async()
+        s.RenderSum(seed=1, sample_count=1)   # the render waits for the upload and switches to the other arena
+        assert s.arena_check() == 0
+    s.close()

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -79,7 +80,7 @@ struct rtc_scene {
     unsigned char* arena_dev[2] = {nullptr, nullptr};
     unsigned char* arena_host = nullptr;  // cudaMallocHost
     size_t arena_bytes = 0;
-    size_t part_off[16] = {0};            // offsets of the scene arrays inside an arena (index = ArenaPart)
+    size_t part_off[24] = {0};            // offsets of the scene arrays inside an arena (index = ArenaPart)
     // Only the head of an arena travels over the host link; its tail -- levels >= 1 of the LCA range-minimum table,
     // the exact boxes of the few leaves that need them, the identity rotations of a scene without rotated
     // primitives: 11 of 35 MB for the 100k dragon -- is a pure function of the head and is rebuilt on the device
@@ -87,6 +88,8 @@ struct rtc_scene {
     size_t upload_bytes = 0;              // size of the head = bytes per H2D copy (and of the pinned mirror)
     size_t sparse_boxes = 0;              // entries of the part ubox_sparse: (slot, min, max) of the leaves with an explicit box
     bool rot_generated = false;           // xf_rot is all identity and lives in the tail
+    // xf_pos / (mat0, mat1) travel as a palette of distinct rows + a 16-bit index per primitive and are expanded on the device
+    size_t xf_palette_rows = 0, mat_palette_rows = 0;
     std::vector<unsigned char> arena_full; // the whole arena as the host would have uploaded it (tests: rtc_scene_arena_check)
     int arena_cur = 0;                    // the arena the next render reads
     DevScene slices{};                    // pointers into arena_dev[arena_cur] (scalars filled by dev())
@@ -247,7 +250,31 @@ namespace {
 // Lays the flat scene arrays out in one arena (256-byte aligned slices): first everything that has to be uploaded, then
 // what the device derives from it.
 enum ArenaPart { A_GEO0, A_GEO1, A_GEO2, A_XF_POS, A_MAT0, A_MAT1, A_INODES, A_RNODES, A_RMETA, A_LIGHTS, A_PLANES, A_PLIGHTS,
-                 A_UBOX_SPARSE, A_XF_ROT, A_LCA, A_UBOX, A_COUNT };
+                 A_UBOX_SPARSE, A_XF_PAL, A_XF_IDX, A_MAT_PAL, A_MAT_IDX, A_XF_ROT, A_LCA, A_UBOX, A_COUNT };
+static_assert(A_COUNT <= 24, "rtc_scene::part_off");
+// distinct rows of a float4 table with `k` float4 per row, and the row index of every entry; empty result = more than 65536
+// distinct rows (the table then travels as it is)
+bool build_palette(const f4* rows0, const f4* rows1, size_t n, std::vector<f4>& palette, std::vector<uint16_t>& index) {
+    struct Key { uint32_t w[8]; bool operator<(const Key& o) const { return std::memcmp(w, o.w, sizeof w) < 0; } };
+    std::map<Key, uint32_t> seen;
+    palette.clear();
+    index.assign(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        Key k;
+        std::memset(&k, 0, sizeof k);
+        std::memcpy(k.w, &rows0[i], 16);
+        if (rows1) std::memcpy(k.w + 4, &rows1[i], 16);
+        auto it = seen.find(k);
+        if (it == seen.end()) {
+            if (seen.size() >= 65536) { palette.clear(); index.clear(); return false; }
+            it = seen.emplace(k, (uint32_t)seen.size()).first;
+            palette.push_back(rows0[i]);
+            if (rows1) palette.push_back(rows1[i]);
+        }
+        index[i] = (uint16_t)it->second;
+    }
+    return true;
+}
 void point_slices(rtc_scene* s, int which) {
     unsigned char* base = s->arena_dev[which];
     const size_t* off = s->part_off;
@@ -268,10 +295,21 @@ int prepare_arena(rtc_scene* s) {
     CU(cudaSetDevice(s->device));
     if (s->arena_host) return RTC_OK;
     const FlatScene& F = s->host.flat;
-    // the leaves whose exact box cannot be read off a single untransformed triangle: (slot, min, max) = 3 float4 each
+    // The device reads ubox only for leaves whose exact box cannot be read off a single untransformed triangle
+    // (rt_device.cuh leaf_test): the arena keeps those, as (slot, min, max) = 3 float4 each, and zeros elsewhere.
+    std::vector<f4> dev_ubox(F.ubox.size(), f4{0.f, 0.f, 0.f, 0.f});
+    for (const RefNode& nd : s->host.nodes) {
+        if (nd.left != UINT32_MAX || nd.count == 0) continue;
+        const Primitive& p0 = s->host.prims[nd.first];
+        const bool ident = p0.rot.x == 0.f && p0.rot.y == 0.f && p0.rot.z == 0.f && p0.rot.w == 1.f && p0.pos.x == 0.f &&
+                           p0.pos.y == 0.f && p0.pos.z == 0.f;
+        if (nd.count == 1 && p0.type == PT_TRIANGLE && ident) continue;   // IREF_FAST (bvh_build.cpp)
+        dev_ubox[2 * (size_t)nd.first] = F.ubox[2 * (size_t)nd.first];
+        dev_ubox[2 * (size_t)nd.first + 1] = F.ubox[2 * (size_t)nd.first + 1];
+    }
     std::vector<f4> sparse;
-    for (size_t i = 0; 2 * i + 1 < F.ubox.size(); ++i) {
-        const f4 &mn = F.ubox[2 * i], &mx = F.ubox[2 * i + 1];
+    for (size_t i = 0; 2 * i + 1 < dev_ubox.size(); ++i) {
+        const f4 &mn = dev_ubox[2 * i], &mx = dev_ubox[2 * i + 1];
         const bool zero = mn.x == 0.f && mn.y == 0.f && mn.z == 0.f && mn.w == 0.f && mx.x == 0.f && mx.y == 0.f && mx.z == 0.f && mx.w == 0.f
                           && !std::signbit(mn.x) && !std::signbit(mn.y) && !std::signbit(mn.z) && !std::signbit(mx.x) && !std::signbit(mx.y) && !std::signbit(mx.z);
         if (zero) continue;
@@ -284,25 +322,38 @@ int prepare_arena(rtc_scene* s) {
     s->rot_generated = !(F.features & FE_ROTATION);   // every rotation is (0, 0, 0, 1)
     for (const f4& q : F.xf_rot)
         if (!(q.x == 0.f && q.y == 0.f && q.z == 0.f && q.w == 1.f) || std::signbit(q.x) || std::signbit(q.y) || std::signbit(q.z)) s->rot_generated = false;
-    struct Part { const void* src; size_t bytes; };
+    std::vector<f4> xf_pal, mat_pal;
+    std::vector<uint16_t> xf_idx, mat_idx;
+    const bool xf_packed = F.xf_pos.size() >= 1024 && build_palette(F.xf_pos.data(), nullptr, F.xf_pos.size(), xf_pal, xf_idx) &&
+                           xf_pal.size() * 8 < F.xf_pos.size();
+    const bool mat_packed = F.mat0.size() >= 1024 && build_palette(F.mat0.data(), F.mat1.data(), F.mat0.size(), mat_pal, mat_idx) &&
+                            mat_pal.size() * 8 < F.mat0.size();
+    s->xf_palette_rows = xf_packed ? xf_pal.size() : 0;
+    s->mat_palette_rows = mat_packed ? mat_pal.size() / 2 : 0;
+    struct Part { const void* src; size_t bytes; bool head; };
     Part parts[A_COUNT];
-    parts[A_GEO0] = {F.geo0.data(), F.geo0.size() * sizeof(f4)};       parts[A_GEO1] = {F.geo1.data(), F.geo1.size() * sizeof(f4)};
-    parts[A_GEO2] = {F.geo2.data(), F.geo2.size() * sizeof(f4)};       parts[A_XF_POS] = {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4)};
-    parts[A_MAT0] = {F.mat0.data(), F.mat0.size() * sizeof(f4)};       parts[A_MAT1] = {F.mat1.data(), F.mat1.size() * sizeof(f4)};
-    parts[A_INODES] = {F.inodes.data(), F.inodes.size() * sizeof(f4)}; parts[A_RNODES] = {F.rnodes.data(), F.rnodes.size() * sizeof(f4)};
-    parts[A_RMETA] = {F.rmeta.data(), F.rmeta.size() * sizeof(u4)};    parts[A_LIGHTS] = {F.lights.data(), F.lights.size() * sizeof(int32_t)};
-    parts[A_PLANES] = {F.planes.data(), F.planes.size() * sizeof(f4)}; parts[A_PLIGHTS] = {F.plights.data(), F.plights.size() * sizeof(f4)};
-    parts[A_UBOX_SPARSE] = {sparse.data(), sparse.size() * sizeof(f4)};
-    parts[A_XF_ROT] = {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4)};
-    parts[A_LCA] = {F.lca.data(), F.lca.size() * sizeof(uint32_t)};
-    parts[A_UBOX] = {F.ubox.data(), F.ubox.size() * sizeof(f4)};
+    parts[A_GEO0] = {F.geo0.data(), F.geo0.size() * sizeof(f4), true};       parts[A_GEO1] = {F.geo1.data(), F.geo1.size() * sizeof(f4), true};
+    parts[A_GEO2] = {F.geo2.data(), F.geo2.size() * sizeof(f4), true};       parts[A_XF_POS] = {F.xf_pos.data(), F.xf_pos.size() * sizeof(f4), !xf_packed};
+    parts[A_MAT0] = {F.mat0.data(), F.mat0.size() * sizeof(f4), !mat_packed}; parts[A_MAT1] = {F.mat1.data(), F.mat1.size() * sizeof(f4), !mat_packed};
+    parts[A_INODES] = {F.inodes.data(), F.inodes.size() * sizeof(f4), true}; parts[A_RNODES] = {F.rnodes.data(), F.rnodes.size() * sizeof(f4), true};
+    parts[A_RMETA] = {F.rmeta.data(), F.rmeta.size() * sizeof(u4), true};    parts[A_LIGHTS] = {F.lights.data(), F.lights.size() * sizeof(int32_t), true};
+    parts[A_PLANES] = {F.planes.data(), F.planes.size() * sizeof(f4), true}; parts[A_PLIGHTS] = {F.plights.data(), F.plights.size() * sizeof(f4), true};
+    parts[A_UBOX_SPARSE] = {sparse.data(), sparse.size() * sizeof(f4), true};
+    parts[A_XF_PAL] = {xf_pal.data(), xf_packed ? xf_pal.size() * sizeof(f4) : 0, true};
+    parts[A_XF_IDX] = {xf_idx.data(), xf_packed ? xf_idx.size() * sizeof(uint16_t) : 0, true};
+    parts[A_MAT_PAL] = {mat_pal.data(), mat_packed ? mat_pal.size() * sizeof(f4) : 0, true};
+    parts[A_MAT_IDX] = {mat_idx.data(), mat_packed ? mat_idx.size() * sizeof(uint16_t) : 0, true};
+    parts[A_XF_ROT] = {F.xf_rot.data(), F.xf_rot.size() * sizeof(f4), !s->rot_generated};
+    parts[A_LCA] = {F.lca.data(), F.lca.size() * sizeof(uint32_t), false};   // its level 0 travels as a second, small copy
+    parts[A_UBOX] = {dev_ubox.data(), dev_ubox.size() * sizeof(f4), false};
     size_t total = 0, head = 0;
-    for (int i = 0; i < A_COUNT; ++i) {
-        s->part_off[i] = total;
-        total += (parts[i].bytes + 255) & ~(size_t)255;
-        // the head ends before the rotations when they are all identity, behind them otherwise; level 0 of the LCA table
-        // (the only level that travels) is a second, small copy
-        if (i < A_XF_ROT || (i == A_XF_ROT && !s->rot_generated)) head = total;
+    for (int pass = 0; pass < 2; ++pass) {   // the parts that travel first, then the ones the device derives from them
+        for (int i = 0; i < A_COUNT; ++i) {
+            if (parts[i].head != (pass == 0)) continue;
+            s->part_off[i] = total;
+            total += (parts[i].bytes + 255) & ~(size_t)255;
+        }
+        if (pass == 0) head = total;
     }
     if (total == 0) total = 256;
     s->arena_full.assign(total, 0);
@@ -346,6 +397,12 @@ int issue_upload(rtc_scene* s, int target, cudaStream_t st) {
     }
     if (s->rot_generated && !F.xf_rot.empty())
         launch_fill_identity_rotations(c, (float4*)(dev + s->part_off[A_XF_ROT]), (uint32_t)F.xf_rot.size());
+    if (s->xf_palette_rows)
+        launch_expand_palette(c, (const float4*)(dev + s->part_off[A_XF_PAL]), (const uint16_t*)(dev + s->part_off[A_XF_IDX]),
+                              (uint32_t)F.xf_pos.size(), (float4*)(dev + s->part_off[A_XF_POS]), nullptr);
+    if (s->mat_palette_rows)
+        launch_expand_palette(c, (const float4*)(dev + s->part_off[A_MAT_PAL]), (const uint16_t*)(dev + s->part_off[A_MAT_IDX]),
+                              (uint32_t)F.mat0.size(), (float4*)(dev + s->part_off[A_MAT0]), (float4*)(dev + s->part_off[A_MAT1]));
     CU(cudaGetLastError());
     return RTC_OK;
 }

@@ -633,6 +633,14 @@ __global__ void __launch_bounds__(256) k_expand_boxes(const float4* sparse, uint
         ubox[2 * (size_t)slot + 1] = sparse[3 * i + 2];
     }
 }
+// per-primitive rows (position | flags, or the two material rows) from the palette of distinct rows that was uploaded
+__global__ void __launch_bounds__(256) k_expand_palette(const float4* palette, const uint16_t* index, uint32_t n, float4* out0, float4* out1) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t row = index[i];
+        if (out1) { out0[i] = palette[2 * row]; out1[i] = palette[2 * row + 1]; }
+        else out0[i] = palette[row];
+    }
+}
 __global__ void __launch_bounds__(256) k_fill_identity_rotations(float4* rot, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) rot[i] = make_float4(0.f, 0.f, 0.f, 1.f);
 }
@@ -757,6 +765,9 @@ void launch_expand_lca(const LaunchCtx& c, uint32_t* lca, const uint4* rmeta, ui
 }
 void launch_expand_boxes(const LaunchCtx& c, const float4* sparse, uint32_t n, float4* ubox) {
     k_expand_boxes<<<grid_for(n, 256, c.sms, 8), 256, 0, c.stream>>>(sparse, n, ubox);
+}
+void launch_expand_palette(const LaunchCtx& c, const float4* palette, const uint16_t* index, uint32_t n, float4* out0, float4* out1) {
+    k_expand_palette<<<grid_for(n, 256, c.sms, 8), 256, 0, c.stream>>>(palette, index, n, out0, out1);
 }
 void launch_fill_identity_rotations(const LaunchCtx& c, float4* rot, uint32_t n) {
     k_fill_identity_rotations<<<grid_for(n, 256, c.sms, 8), 256, 0, c.stream>>>(rot, n);

@@ -32,6 +32,7 @@ void launch_fold(const LaunchCtx& c, const float4* accum4, float* accum, uint32_
 void launch_expand_lca(const LaunchCtx& c, uint32_t* lca, const uint4* rmeta, uint32_t n, uint32_t levels);
 void launch_expand_boxes(const LaunchCtx& c, const float4* sparse, uint32_t n, float4* ubox);
 void launch_fill_identity_rotations(const LaunchCtx& c, float4* rot, uint32_t n);
+void launch_expand_palette(const LaunchCtx& c, const float4* palette, const uint16_t* index, uint32_t n, float4* out0, float4* out1);
 void launch_tally(const LaunchCtx& c, const uint32_t* q, const uint32_t* tqc, uint32_t ray_depth, unsigned long long* stats);
 void launch_resolve(const LaunchCtx& c, const float* accum, float inv_samples, uint32_t nvalues, uint8_t* out);
 void launch_tonemap(const LaunchCtx& c, const float* rgb, uint32_t nvalues, uint8_t* out);

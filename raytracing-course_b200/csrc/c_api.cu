@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -247,6 +248,18 @@ struct rtc_scene {
 
 namespace {
 
+// RTC_TIMING=1: phase times of scene creation on stderr (the host build prints its own phases, bvh_build.cpp)
+struct Lap {
+    bool on = std::getenv("RTC_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void operator()(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rtc timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // Lays the flat scene arrays out in one arena (256-byte aligned slices): first everything that has to be uploaded, then
 // what the device derives from it.
 enum ArenaPart { A_GEO0, A_GEO1, A_GEO2, A_XF_POS, A_MAT0, A_MAT1, A_INODES, A_RNODES, A_RMETA, A_LIGHTS, A_PLANES, A_PLIGHTS,
@@ -294,6 +307,7 @@ int prepare_arena(rtc_scene* s) {
     if (s->device < 0) return fail(RTC_ERR_NO_DEVICE, "scene has no CUDA device");
     CU(cudaSetDevice(s->device));
     if (s->arena_host) return RTC_OK;
+    Lap lap;
     const FlatScene& F = s->host.flat;
     // The device reads ubox only for leaves whose exact box cannot be read off a single untransformed triangle
     // (rt_device.cuh leaf_test): the arena keeps those, as (slot, min, max) = 3 float4 each, and zeros elsewhere.
@@ -328,6 +342,7 @@ int prepare_arena(rtc_scene* s) {
                            xf_pal.size() * 8 < F.xf_pos.size();
     const bool mat_packed = F.mat0.size() >= 1024 && build_palette(F.mat0.data(), F.mat1.data(), F.mat0.size(), mat_pal, mat_idx) &&
                             mat_pal.size() * 8 < F.mat0.size();
+    lap("arena: sparse boxes, palettes");
     s->xf_palette_rows = xf_packed ? xf_pal.size() : 0;
     s->mat_palette_rows = mat_packed ? mat_pal.size() / 2 : 0;
     struct Part { const void* src; size_t bytes; bool head; };
@@ -361,6 +376,7 @@ int prepare_arena(rtc_scene* s) {
         if (parts[i].bytes) std::memcpy(s->arena_full.data() + s->part_off[i], parts[i].src, parts[i].bytes);
     s->upload_bytes = head;
     s->arena_bytes = total;
+    lap("arena: host image");
     CU(cudaMalloc(&s->arena_dev[0], total));
     CU(cudaMemset(s->arena_dev[0], 0, total));   // the padding between the device-built parts is never written again
     // pinned mirror of what travels: the head, and level 0 of the LCA table right behind it
@@ -378,6 +394,7 @@ int prepare_arena(rtc_scene* s) {
     CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CU(s->stats.ensure(kStatWords));
     CU(cudaMemset(s->stats.p, 0, kStatWords * sizeof(unsigned long long)));
+    lap("arena: cudaMalloc, pinned mirror");
     return RTC_OK;
 }
 // H2D copies of the head (+ LCA level 0) into arena `target`, then the device-side rebuild of the tail; all on `st`
@@ -410,9 +427,11 @@ int issue_upload(rtc_scene* s, int target, cudaStream_t st) {
 int upload_scene(rtc_scene* s, uint64_t* h2d) {
     int rc = prepare_arena(s);
     if (rc) return rc;
+    Lap lap;
     CU(cudaDeviceSynchronize());   // nothing may still be reading the arena
     if ((rc = issue_upload(s, s->arena_cur, s->copy_stream))) return rc;
     CU(cudaStreamSynchronize(s->copy_stream));
+    lap("upload + device-built tail");
     s->arena_pending = false;
     if (h2d) *h2d = s->device_bytes;
     return RTC_OK;
@@ -460,10 +479,13 @@ rtc_scene* make_scene(const std::string& text, int device, int dialect = DIALECT
         return nullptr;
     }
     rtc_scene* s = new rtc_scene();
+    Lap lap;
     try {
         s->host.dialect = dialect;
         s->host.parse(text);
+        lap("scene text -> primitives");
         s->host.init();
+        lap("host build (sum of the above)");
     } catch (const std::exception& e) {
         fail(RTC_ERR_UNSUPPORTED, e.what());
         delete s;
@@ -571,8 +593,10 @@ rtc_scene* rtc_scene_load_dialect(const char* path, int device, int dialect) {
     if (!path) { fail(RTC_ERR_ARG, "null path"); return nullptr; }
     std::ifstream in(path, std::ios::binary);
     if (!in) { fail(RTC_ERR_IO, std::string("cannot open scene file ") + path); return nullptr; }
+    Lap lap;
     std::ostringstream ss;
     ss << in.rdbuf();
+    lap("read scene file");
     return make_scene(ss.str(), device, dialect);
 }
 rtc_scene* rtc_scene_load(const char* path, int device) { return rtc_scene_load_dialect(path, device, DIALECT_HW5); }

@@ -15,10 +15,12 @@
 //    of the NEW_PRIMITIVE line) -- in practice only a following NEW_PRIMITIVE matters;
 //  * a shape line (PLANE/BOX/ELLIPSOID/TRIANGLE) resets every attribute given before it;
 //  * unknown scene-level words are reported on stderr and skipped.
+#include <charconv>
 #include <cstdio>
 #include <functional>
 #include <sstream>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 
 #include "scene_host.h"
@@ -45,26 +47,71 @@ template <class F>
 struct Word {
     F fn;
     int first, last;  // dialects that know this word
+    // Fast form of a primitive attribute (nearly every line of a 100k-triangle scene is one): the word takes `nfloat`
+    // floats; when the line holds that many PLAIN decimal numbers (plain_float below) they are converted with
+    // std::from_chars and handed to fn through a stream-free twin.  Anything else -- a missing, malformed or
+    // out-of-range argument -- goes through operator>> as before, so that the partial-failure behaviour of the
+    // reference's reader (sceneload.cpp uses operator>> throughout) is kept by construction.
+    int nfloat = -1;
+    void (*fast)(const float*, Primitive&) = nullptr;
     bool known(int dialect) const { return first <= dialect && dialect <= last; }
 };
 
+// [+-]digits[.digits][(e|E)[+-]digits] with at least one digit in the mantissa: the subset of what operator>>(float&)
+// accepts (libstdc++ num_get -> strtof) on which std::from_chars gives the same, correctly rounded, value
+bool plain_float(const char* b, const char* e, float& out) {
+    const char* p = b;
+    if (p < e && (*p == '+' || *p == '-')) ++p;
+    int nd = 0;
+    while (p < e && *p >= '0' && *p <= '9') { ++p; ++nd; }
+    if (p < e && *p == '.') { ++p; while (p < e && *p >= '0' && *p <= '9') { ++p; ++nd; } }
+    if (nd == 0) return false;
+    if (p < e && (*p == 'e' || *p == 'E')) {
+        ++p;
+        if (p < e && (*p == '+' || *p == '-')) ++p;
+        int ne = 0;
+        while (p < e && *p >= '0' && *p <= '9') { ++p; ++ne; }
+        if (ne == 0) return false;
+    }
+    if (p != e) return false;
+    if (*b == '+') ++b;   // from_chars takes no leading plus
+    const std::from_chars_result r = std::from_chars(b, e, out);
+    return r.ec == std::errc() && r.ptr == e;   // over- / underflow: let operator>> decide
+}
+bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; }   // the classic locale's
+// the first `n` whitespace-separated tokens after `p` as plain floats
+bool plain_floats(const char* p, const char* end, int n, float* out) {
+    for (int i = 0; i < n; ++i) {
+        while (p < end && is_space(*p)) ++p;
+        const char* b = p;
+        while (p < end && !is_space(*p)) ++p;
+        if (b == p || !plain_float(b, p, out[i])) return false;
+    }
+    return true;
+}
+
 const std::unordered_map<std::string, Word<PrimFn>>& prim_table() {
     static const std::unordered_map<std::string, Word<PrimFn>> t = {
-        {"ELLIPSOID", {[](std::istream& in, Primitive& p) { vec3 r{0, 0, 0}; in >> r; p = shaped(PT_ELLIPSOID, r); }, 1, 5}},
-        {"PLANE", {[](std::istream& in, Primitive& p) { vec3 n{0, 0, 0}; in >> n; p = shaped(PT_PLANE, n); }, 1, 5}},
-        {"BOX", {[](std::istream& in, Primitive& p) { vec3 s{0, 0, 0}; in >> s; p = shaped(PT_BOX, s); }, 1, 5}},
+        {"ELLIPSOID", {[](std::istream& in, Primitive& p) { vec3 r{0, 0, 0}; in >> r; p = shaped(PT_ELLIPSOID, r); }, 1, 5,
+                       3, [](const float* f, Primitive& p) { p = shaped(PT_ELLIPSOID, vec3{f[0], f[1], f[2]}); }}},
+        {"PLANE", {[](std::istream& in, Primitive& p) { vec3 n{0, 0, 0}; in >> n; p = shaped(PT_PLANE, n); }, 1, 5,
+                   3, [](const float* f, Primitive& p) { p = shaped(PT_PLANE, vec3{f[0], f[1], f[2]}); }}},
+        {"BOX", {[](std::istream& in, Primitive& p) { vec3 s{0, 0, 0}; in >> s; p = shaped(PT_BOX, s); }, 1, 5,
+                 3, [](const float* f, Primitive& p) { p = shaped(PT_BOX, vec3{f[0], f[1], f[2]}); }}},
         {"TRIANGLE", {[](std::istream& in, Primitive& p) {
              vec3 a{0, 0, 0}, b{0, 0, 0}, c{0, 0, 0};
              in >> a >> b >> c;
              p = shaped(PT_TRIANGLE, a, b, c);
-         }, 5, 5}},
-        {"COLOR", {[](std::istream& in, Primitive& p) { in >> p.col; }, 1, 5}},
-        {"POSITION", {[](std::istream& in, Primitive& p) { in >> p.pos; }, 1, 5}},
-        {"ROTATION", {[](std::istream& in, Primitive& p) { in >> p.rot; }, 1, 5}},
+         }, 5, 5,
+         9, [](const float* f, Primitive& p) { p = shaped(PT_TRIANGLE, vec3{f[0], f[1], f[2]}, vec3{f[3], f[4], f[5]}, vec3{f[6], f[7], f[8]}); }}},
+        {"COLOR", {[](std::istream& in, Primitive& p) { in >> p.col; }, 1, 5, 3, [](const float* f, Primitive& p) { p.col = vec3{f[0], f[1], f[2]}; }}},
+        {"POSITION", {[](std::istream& in, Primitive& p) { in >> p.pos; }, 1, 5, 3, [](const float* f, Primitive& p) { p.pos = vec3{f[0], f[1], f[2]}; }}},
+        {"ROTATION", {[](std::istream& in, Primitive& p) { in >> p.rot; }, 1, 5,
+                      4, [](const float* f, Primitive& p) { p.rot.x = f[0]; p.rot.y = f[1]; p.rot.z = f[2]; p.rot.w = f[3]; }}},
         {"METALLIC", {[](std::istream&, Primitive& p) { p.material = MAT_METALLIC; }, 2, 5}},
         {"DIELECTRIC", {[](std::istream&, Primitive& p) { p.material = MAT_DIELECTRIC; }, 2, 5}},
-        {"IOR", {[](std::istream& in, Primitive& p) { in >> p.ior; }, 2, 5}},
-        {"EMISSION", {[](std::istream& in, Primitive& p) { in >> p.emission; }, 3, 5}},
+        {"IOR", {[](std::istream& in, Primitive& p) { in >> p.ior; }, 2, 5, 1, [](const float* f, Primitive& p) { p.ior = f[0]; }}},
+        {"EMISSION", {[](std::istream& in, Primitive& p) { in >> p.emission; }, 3, 5, 3, [](const float* f, Primitive& p) { p.emission = vec3{f[0], f[1], f[2]}; }}},
     };
     return t;
 }
@@ -96,20 +143,57 @@ const std::unordered_map<std::string, Word<LightFn>>& light_table() {
     return t;
 }
 
+// std::getline over the scene text without copying it: lines end at '\n', the last one may lack it
+struct Lines {
+    const char* p;
+    const char* end;
+    bool next(std::string_view& line) {
+        if (p >= end) return false;
+        const char* e = p;
+        while (e < end && *e != '\n') ++e;
+        line = std::string_view(p, (size_t)(e - p));
+        p = e < end ? e + 1 : e;
+        return true;
+    }
+};
+// the first word of a line, as `ls >> word` reads it
+std::string_view first_word(std::string_view line, const char*& rest) {
+    const char* p = line.data();
+    const char* end = p + line.size();
+    while (p < end && is_space(*p)) ++p;
+    const char* b = p;
+    while (p < end && !is_space(*p)) ++p;
+    rest = p;
+    return std::string_view(b, (size_t)(p - b));
+}
+template <class Item>
+bool try_fast(const Word<std::function<void(std::istream&, Item&)>>&, const char*, const char*, Item&) { return false; }
+bool try_fast(const Word<PrimFn>& w, const char* rest, const char* end, Primitive& item) {
+    if (!w.fast) return false;
+    float f[9];
+    if (!plain_floats(rest, end, w.nfloat, f)) return false;
+    w.fast(f, item);
+    return true;
+}
+
 // Reads one NEW_PRIMITIVE / NEW_LIGHT block.  Returns the word that ended the block ("" for blank line / EOF).
-// `ls` is one line stream reused for every line of the file (constructing an istringstream per line was half of the
-// time to read a 100k-triangle scene); clear() + str() give it exactly the state of a fresh one.
+// `ls` is one line stream reused for every line that needs operator>> (constructing an istringstream per line was half
+// of the time to read a 100k-triangle scene; a line of plain numbers needs none: try_fast); clear() + str() give it
+// exactly the state of a fresh one.
 template <class Table, class Item>
-std::string read_block(std::istream& in, std::istringstream& ls, const Table& table, int dialect, Item& item) {
-    std::string line, word;
-    while (std::getline(in, line)) {
-        ls.clear();
-        ls.str(line);
-        word.clear();
-        ls >> word;
+std::string read_block(Lines& in, std::istringstream& ls, const Table& table, int dialect, Item& item) {
+    std::string_view line;
+    std::string key;
+    while (in.next(line)) {
+        const char* rest;
+        const std::string_view word = first_word(line, rest);
         if (word.empty()) return "";
-        auto it = table.find(word);
-        if (it == table.end() || !it->second.known(dialect)) return word;
+        key.assign(word.data(), word.size());
+        auto it = table.find(key);
+        if (it == table.end() || !it->second.known(dialect)) return key;
+        if (try_fast(it->second, rest, line.data() + line.size(), item)) continue;
+        ls.clear();
+        ls.str(std::string(rest, (size_t)(line.data() + line.size() - rest)));   // the stream right after `ls >> word`
         it->second.fn(ls, item);
     }
     return "";
@@ -118,14 +202,16 @@ std::string read_block(std::istream& in, std::istringstream& ls, const Table& ta
 }  // namespace
 
 void HostScene::parse(const std::string& text) {
-    std::istringstream in(text);
+    Lines in{text.data(), text.data() + text.size()};
     std::istringstream ls, block_ls;
-    std::string line, word;
-    while (std::getline(in, line)) {
+    std::string_view line;
+    std::string word;
+    while (in.next(line)) {
+        const char* rest;
+        const std::string_view w = first_word(line, rest);
+        word.assign(w.data(), w.size());
         ls.clear();
-        ls.str(line);
-        word.clear();
-        ls >> word;
+        ls.str(std::string(rest, (size_t)(line.data() + line.size() - rest)));
         while (!word.empty()) {
             const bool new_prim = word == "NEW_PRIMITIVE", new_light = word == "NEW_LIGHT" && dialect == DIALECT_HW2;
             if (new_prim || new_light) {

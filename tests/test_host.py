@@ -168,6 +168,23 @@ def test_parser_quirks_match_reference_golden(rtc):
     assert i == 4
 
 
+def test_parser_number_formats_match_reference_golden(rtc):
+    """Number formats at the edge of the reader's fast path (plain decimals via std::from_chars, everything else via
+    operator>>): signs, bare dots, exponents, hex, inf / nan, trailing garbage, commas, over- and underflow, CRLF --
+    against what the REFERENCE made of the same texts (tools/make_golden.py parser_numbers)."""
+    g = golden("parser_numbers")
+    i = 0
+    while "text%d" % i in g:
+        s = rtc.Scene(text=g["text%d" % i].tobytes(), device=-1)
+        assert [s.width, s.height, s.ray_depth, s.samples, s.nprims, s.nbvh, s.nnodes, s.nlights] == g["info%d" % i].tolist(), i
+        tm, d = s.prims()
+        assert np.array_equal(tm, g["tm%d" % i]), i
+        assert np.array_equal(d, g["data%d" % i]), (i, np.argwhere(d != g["data%d" % i]).tolist())
+        s.close()
+        i += 1
+    assert i == 2
+
+
 def test_bench_configs_and_reference_arm(tmp_path):
     """bench.py: every BASELINE.json configuration resolves to its scene / size, and the reference arm prints the
     contract's JSON line (a tiny sample here: 8x8 pixels, 1 spp of the 10k dragon through the compiled reference)."""

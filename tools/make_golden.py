@@ -258,6 +258,40 @@ def parser_fixture():
     print("parser fixture:", len(PARSER_TEXTS), "texts")
 
 
+# Number formats at the edge of the product reader's fast path (scene_load.cpp plain_float: plain decimal numbers are
+# converted with std::from_chars, everything else goes through operator>> like the reference's whole reader).  Every
+# value a failed read would leave untouched is defined by an earlier line, so nothing here is indeterminate.
+NUMBER_TEXTS = [
+    "DIMENSIONS 2 2\nSAMPLES 1\nRAY_DEPTH 1\n"
+    "NEW_PRIMITIVE\nBOX 1. .5 +2\nPOSITION 5 6 7\nPOSITION 1.5abc 2 3\nCOLOR 0.1 0.2 0.3\nCOLOR 1E+0 2e-1 3E0\nEMISSION 0 0 0\n\n"
+    "NEW_PRIMITIVE\nELLIPSOID 1 1 1\nPOSITION 1 2 3\nPOSITION 0x10 5 5\nCOLOR 0.5 0.5 0.5\nCOLOR inf 1 1\nEMISSION 1 2 3\nEMISSION nan 4 4\n\n"
+    "NEW_PRIMITIVE\nBOX 1 1 1\nPOSITION 1 2 3\nPOSITION 1,5 9 9\nCOLOR 0.25 0.25 0.25\nCOLOR --1 2 2\nEMISSION 0 0 0\nIOR 1.25\nIOR 1e\n\n"
+    "NEW_PRIMITIVE\nBOX 1 1 1\nPOSITION 1 2 3\nCOLOR 0.5 0.5 0.5\nCOLOR 1e400 0.75 0.75\nEMISSION 0.5 0.5 0.5\nEMISSION 1e-50 0.25 0.25\nIOR 2.5\nIOR 1e+\n\n"
+    "NEW_PRIMITIVE\nBOX 1 1 1\nPOSITION -0 -.5e1 00012.5000\nCOLOR 1 1 1\nCOLOR 0.1234567890123456789 1e-3 123456789\nEMISSION 0 0 0\nROTATION 0 0 0 1\nROTATION 0.5 .5 5e-1 +0.5\n",
+    # CRLF line ends: the carriage return is white space to operator>>, a line of just \r ends a block
+    "DIMENSIONS 2 2\r\nSAMPLES 1\r\nRAY_DEPTH 1\r\nNEW_PRIMITIVE\r\nBOX 1 2 3\r\nPOSITION 0 0 0\r\nCOLOR 0.5 0.25 1\r\nEMISSION 0 0 0\r\nMETALLIC\r\n\r\n"
+    "NEW_PRIMITIVE\r\nPLANE 0 1 0\r\nPOSITION 0 -1 0\r\nCOLOR 1 1 1\r\nEMISSION 0 0 0\r\n",
+]
+
+
+def parser_number_fixture():
+    import tempfile
+    out = {}
+    for i, text in enumerate(NUMBER_TEXTS):
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False, newline="") as f:
+            f.write(text)
+        s = orclib.Scene(orclib.ref(), f.name)
+        tm, data = s.prims()
+        out["text%d" % i] = np.frombuffer(text.encode(), np.uint8)
+        out["info%d" % i] = np.array([s.width, s.height, s.ray_depth, s.samples, s.nprims, s.nbvh, s.nnodes, s.nlights])
+        out["tm%d" % i] = tm
+        out["data%d" % i] = data
+        s.close()
+        os.unlink(f.name)
+    np.savez_compressed(os.path.join(GOLD, "parser_numbers.npz"), **out)
+    print("parser number fixture:", len(NUMBER_TEXTS), "texts")
+
+
 def headline():
     """The headline scenes pinned to the reference itself (round 2): golden rays of the three 100k dragons (primary,
     first-bounce secondary and random rays through librefprobe -> Scene::RayIntersection) and one larger converged
@@ -313,5 +347,7 @@ if __name__ == "__main__":
         dialects()
     elif len(sys.argv) > 1 and sys.argv[1] == "headline":
         headline()
+    elif len(sys.argv) > 1 and sys.argv[1] == "parser_numbers":
+        parser_number_fixture()
     else:
         main()

@@ -563,7 +563,7 @@ int ensure_wavefront(rtc_scene* s, uint64_t cap, int nlanes) {
         if (!l.done) CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         for (auto& set : l.path) for (auto& b : set) CU(b.ensure(cap));
         for (auto& b : l.hit_id) CU(b.ensure(cap));
-        CU(l.trav_queue.ensure(cap));
+        CU(l.trav_queue.ensure(cap * kTraverseQueueWords));
         CU(l.queue.ensure(4 * kMaxDepthSlots));
     }
     return RTC_OK;
@@ -698,7 +698,7 @@ int rtc_intersect_dev(rtc_scene* s, long n, const float* o_dev, const float* d_d
     if ((uint64_t)n > (1ull << 28)) return fail(RTC_ERR_ARG, "too many rays in one call (limit 2^28)");
     rtc_scene::Probe& pb = s->probe;
     CU(pb.ray[0].ensure((size_t)n)); CU(pb.ray[1].ensure((size_t)n));
-    CU(pb.hit.ensure((size_t)n)); CU(pb.tq.ensure((size_t)n)); CU(pb.q.ensure(4));   // q: rays (front, back = 0), traverse count, cursor
+    CU(pb.hit.ensure((size_t)n)); CU(pb.tq.ensure((size_t)n * kTraverseQueueWords)); CU(pb.q.ensure(4));   // q: rays (front, back = 0), traverse count, cursor
     cudaStream_t st = (cudaStream_t)stream;
     PathSoA P{pb.ray[0].p, pb.ray[1].p, nullptr};
     HitSoA H{pb.hit.p};

@@ -19,6 +19,12 @@ constexpr unsigned kFullMask = 0xFFFFFFFFu;
 #ifndef RTC_TRAVERSE_CHUNK
 #define RTC_TRAVERSE_CHUNK 64
 #endif
+#ifndef RTC_TQ_PREFETCH
+#define RTC_TQ_PREFETCH 0
+#endif
+#ifndef RTC_SHADE_PREFETCH
+#define RTC_SHADE_PREFETCH 0
+#endif
 #ifndef RTC_TRAVERSE_CHUNK_DIV
 #define RTC_TRAVERSE_CHUNK_DIV 4
 #endif
@@ -67,7 +73,18 @@ RT_D uint32_t pre_step(const DevScene& S, vec3 o, vec3 d, float& cd, uint32_t& i
 constexpr uint32_t kTqSlotBits = 28;
 constexpr uint32_t kTqSlotMask = (1u << kTqSlotBits) - 1u;
 // warp-aggregated append of slot `i` to the traverse queue; call with the full warp converged
-RT_D void enqueue(uint32_t rootmask, uint32_t i, uint32_t* tq, uint32_t* tq_count, uint32_t lane) {
+// one traverse-queue entry (rt_kernels.h kTraverseQueueWords)
+RT_D void tq_store(uint32_t* tq, uint32_t at, uint32_t entry, vec3 o, vec3 d, float cd) {
+#if RTC_TQ_RECORDS
+    float4* rec = reinterpret_cast<float4*>(tq) + 2 * (size_t)at;
+    WF_ST(rec, make_float4(o.x, o.y, o.z, __uint_as_float(entry)));
+    WF_ST(rec + 1, make_float4(d.x, d.y, d.z, cd));
+#else
+    (void)o; (void)d; (void)cd;
+    WF_ST(tq + at, entry);
+#endif
+}
+RT_D void enqueue(uint32_t rootmask, uint32_t i, vec3 o, vec3 d, float cd, uint32_t* tq, uint32_t* tq_count, uint32_t lane) {
     const bool enters = rootmask != 0;
     unsigned mask = __ballot_sync(kFullMask, enters);
     if (mask) {
@@ -75,7 +92,7 @@ RT_D void enqueue(uint32_t rootmask, uint32_t i, uint32_t* tq, uint32_t* tq_coun
         if (lane == 0) base = atomicAdd(tq_count, (uint32_t)__popc(mask));
         base = __shfl_sync(kFullMask, base, 0);
         const uint32_t entry = i | (rootmask << kTqSlotBits);
-        if (enters) WF_ST(tq + base + __popc(mask & ((1u << lane) - 1u)), entry);
+        if (enters) tq_store(tq, base + __popc(mask & ((1u << lane) - 1u)), entry, o, d, cd);
     }
 }
 
@@ -112,6 +129,8 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, HitSoA 
     const uint32_t rounded = (count + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         uint32_t enters = 0;
+        vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+        float cd = 0.f;
         if (i < count) {
             uint64_t pid = first_path + i;
             uint32_t sample = sample_begin + (uint32_t)(pid / npix);
@@ -123,16 +142,15 @@ __global__ void __launch_bounds__(256) k_generate(DevScene S, PathSoA P, HitSoA 
             // hw3's Camera::GetToRay(float, float) still adds the half pixel of its integer ancestor
             // (hw3 src/scene.cpp:186-187): its jittered samples cover [x + 0.5, x + 1.5)
             if (S.dialect == DIALECT_HW3) { fx = __fadd_rn(fx, 0.5f); fy = __fadd_rn(fy, 0.5f); }
-            vec3 o, d;
             camera_ray(S, fx, fy, o, d);
-            float cd; uint32_t id;
+            uint32_t id;
             enters = pre_step(S, o, d, cd, id);
             WF_ST(P.o + i, make_float4(o.x, o.y, o.z, __uint_as_float(sample)));
             WF_ST(P.d + i, make_float4(d.x, d.y, d.z, cd));
             WF_ST(P.beta + i, make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel)));
             WF_ST(H.id + i, id);
         }
-        enqueue(enters, i, tq, tq_count, lane);
+        enqueue(enters, i, o, d, cd, tq, tq_count, lane);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) q[0] = count;
 }
@@ -147,14 +165,17 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
     const uint32_t rounded = (count + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         uint32_t enters = 0;
+        vec3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+        float cd = 0.f;
         if (i < count) {
-            float cd; uint32_t id;
+            uint32_t id;
             const float4 d4 = WF_LD(P.d + i);
-            enters = pre_step(S, ld3(WF_LD(P.o + i)), ld3(d4), cd, id);
+            o = ld3(WF_LD(P.o + i)); d = ld3(d4);
+            enters = pre_step(S, o, d, cd, id);
             WF_ST(P.d + i, make_float4(d4.x, d4.y, d4.z, cd));
             WF_ST(H.id + i, id);
         }
-        enqueue(enters, i, tq, tq_count, lane);
+        enqueue(enters, i, o, d, cd, tq, tq_count, lane);
     }
 }
 
@@ -349,11 +370,25 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             }
             uint32_t rank = __popc(mR & lt_mask);
             uint32_t serve = min((uint32_t)nR, pool_left);
+#if RTC_TQ_RECORDS && RTC_TQ_PREFETCH
+            // the records the NEXT refill from this chunk will take, on their way while the rays of this one are traversed
+            if (serve + lane < pool_left)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(tq) + 2 * (size_t)(pool_base + serve + lane)));
+#endif
             if (canR && rank < serve) {
+#if RTC_TQ_RECORDS
+                // the entry IS the ray: one coalesced round trip (consecutive ranks read consecutive 32-byte records)
+                const float4* rec32 = reinterpret_cast<const float4*>(tq) + 2 * (size_t)(pool_base + rank);
+                const float4 o4 = WF_LD(rec32), d4 = WF_LD(rec32 + 1);
+                const uint32_t entry = __float_as_uint(o4.w);
+                ray = entry & kTqSlotMask;
+                o = ld3(o4);
+#else
                 const uint32_t entry = WF_LD(tq + pool_base + rank);
                 ray = entry & kTqSlotMask;
                 o = ld3(WF_LD(P.o + ray));
                 const float4 d4 = WF_LD(P.d + ray);
+#endif
                 d = ld3(d4);
                 cd0 = d4.w;
                 inv = ray_inv(d);
@@ -458,6 +493,18 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
         vec3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0), beta = mk3(0, 0, 0);
         uint32_t pixel = 0, sample = 0;
         uint32_t i; bool back;
+#if RTC_SHADE_PREFETCH
+        {   // the state this thread reads in its next iteration, on its way from HBM to the L2
+            uint32_t i2; bool back2;
+            const uint32_t at2 = at + gridDim.x * blockDim.x;
+            if (at2 < view.total && queue_slot(view, at2, cap, i2, back2)) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.o + i2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.d + i2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.beta + i2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(H.id + i2));
+            }
+        }
+#endif
         if (queue_slot(view, at, cap, i, back)) {
             const float4 b4 = WF_LD(P.beta + i), o4 = WF_LD(P.o + i);
             beta = ld3(b4);
@@ -573,7 +620,7 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
             }
             if (emask) {
                 tbase = __shfl_sync(kFullMask, tbase, 0);
-                if (enters) WF_ST(tq + tbase + __popc(emask & lt), dst | (enters << kTqSlotBits));
+                if (enters) tq_store(tq, tbase + __popc(emask & lt), dst | (enters << kTqSlotBits), no, nd, cd);
             }
         }
     }

@@ -7,6 +7,15 @@
 
 namespace rtc {
 
+// Words per traverse-queue entry.  8 (RTC_TQ_RECORDS, the default): an entry is the ray itself -- (origin, bits(slot |
+// entered root children)) (direction, closest-plane distance) -- written by the kernel that makes the ray while it is
+// still in registers, so that a refill of k_traverse is ONE coalesced round trip instead of two dependent ones (queue
+// word, then the scattered path state).  1: the queue word alone.
+#ifndef RTC_TQ_RECORDS
+#define RTC_TQ_RECORDS 1
+#endif
+constexpr uint32_t kTraverseQueueWords = RTC_TQ_RECORDS ? 8 : 1;
+
 struct LaunchCtx {
     cudaStream_t stream;
     int sms;  // multiprocessor count of the device (grid sizing)

@@ -471,11 +471,12 @@ def build_rooflines(scene, args, cnt, stats, lanes, prof, ms_profiled, peaks):
     kname_trav = "k_traverse" if args.traversal == 0 else "k_extend_reftree"
     spec = {
         # key: (kernel, bound, algorithmic bytes per unit, units in the timed region, unit name)
-        "traverse": (kname_trav, "l2", 4 + 32 + 4 + node_bytes * visits_per_ray + 48 * tests_per_ray, trav0, "ray entering the BVH"),
-        # streamed state only: 52 B in, (48 + 4 + 4 * enter) B out per surviving ray; the winner's geometry and material
+        # a traverse-queue entry is the ray itself (32 B: origin | queue word, direction | plane distance), read once; 4 B of hit id out
+        "traverse": (kname_trav, "l2", 32 + 4 + node_bytes * visits_per_ray + 48 * tests_per_ray, trav0, "ray entering the BVH"),
+        # streamed state only: 52 B in, (48 + 4 + 32 * enter) B out per surviving ray; the winner's geometry and material
         # rows (80 B) are L2-resident and not counted
-        "shade": ("k_shade", "hbm", 52 + (52 + 4 * enter) * survive, rays0, "ray"),
-        "generate": ("k_generate", "hbm", 52 + 4 * enter, paths0, "camera path"),
+        "shade": ("k_shade", "hbm", 52 + (52 + 32 * enter) * survive, rays0, "ray"),
+        "generate": ("k_generate", "hbm", 52 + 32 * enter, paths0, "camera path"),
     }
     out = {}
     for key, (kname, bound, bpu, units, uname) in spec.items():

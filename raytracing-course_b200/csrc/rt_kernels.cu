@@ -19,12 +19,6 @@ constexpr unsigned kFullMask = 0xFFFFFFFFu;
 #ifndef RTC_TRAVERSE_CHUNK
 #define RTC_TRAVERSE_CHUNK 64
 #endif
-#ifndef RTC_TQ_PREFETCH
-#define RTC_TQ_PREFETCH 0
-#endif
-#ifndef RTC_SHADE_PREFETCH
-#define RTC_SHADE_PREFETCH 0
-#endif
 #ifndef RTC_TRAVERSE_CHUNK_DIV
 #define RTC_TRAVERSE_CHUNK_DIV 4
 #endif
@@ -370,11 +364,6 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             }
             uint32_t rank = __popc(mR & lt_mask);
             uint32_t serve = min((uint32_t)nR, pool_left);
-#if RTC_TQ_RECORDS && RTC_TQ_PREFETCH
-            // the records the NEXT refill from this chunk will take, on their way while the rays of this one are traversed
-            if (serve + lane < pool_left)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(tq) + 2 * (size_t)(pool_base + serve + lane)));
-#endif
             if (canR && rank < serve) {
 #if RTC_TQ_RECORDS
                 // the entry IS the ray: one coalesced round trip (consecutive ranks read consecutive 32-byte records)
@@ -493,18 +482,6 @@ __global__ void __launch_bounds__(RTC_SHADE_THREADS, (FEAT & (FE_ROTATION | FE_E
         vec3 no = mk3(0, 0, 0), nd = mk3(0, 0, 0), beta = mk3(0, 0, 0);
         uint32_t pixel = 0, sample = 0;
         uint32_t i; bool back;
-#if RTC_SHADE_PREFETCH
-        {   // the state this thread reads in its next iteration, on its way from HBM to the L2
-            uint32_t i2; bool back2;
-            const uint32_t at2 = at + gridDim.x * blockDim.x;
-            if (at2 < view.total && queue_slot(view, at2, cap, i2, back2)) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.o + i2));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.d + i2));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.beta + i2));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(H.id + i2));
-            }
-        }
-#endif
         if (queue_slot(view, at, cap, i, back)) {
             const float4 b4 = WF_LD(P.beta + i), o4 = WF_LD(P.o + i);
             beta = ld3(b4);

@@ -69,14 +69,9 @@ constexpr uint32_t kTqSlotMask = (1u << kTqSlotBits) - 1u;
 // warp-aggregated append of slot `i` to the traverse queue; call with the full warp converged
 // one traverse-queue entry (rt_kernels.h kTraverseQueueWords)
 RT_D void tq_store(uint32_t* tq, uint32_t at, uint32_t entry, vec3 o, vec3 d, float cd) {
-#if RTC_TQ_RECORDS
     float4* rec = reinterpret_cast<float4*>(tq) + 2 * (size_t)at;
     WF_ST(rec, make_float4(o.x, o.y, o.z, __uint_as_float(entry)));
     WF_ST(rec + 1, make_float4(d.x, d.y, d.z, cd));
-#else
-    (void)o; (void)d; (void)cd;
-    WF_ST(tq + at, entry);
-#endif
 }
 RT_D void enqueue(uint32_t rootmask, uint32_t i, vec3 o, vec3 d, float cd, uint32_t* tq, uint32_t* tq_count, uint32_t lane) {
     const bool enters = rootmask != 0;
@@ -184,23 +179,12 @@ __global__ void __launch_bounds__(256) k_pre(DevScene S, PathSoA P, HitSoA H, co
 // next ray at once).  Every iteration the warp votes and executes the kind most
 // lanes are ready for, which keeps lanes busy although rays need between one and several
 // hundred node visits.  `cursor` hands out queue slots, kChunk per atomic.
-// RTC_SMEM_STACK=1 (experiment, off: measured slower): the traversal stack of a lane in shared memory, word w of thread t
-// at [w][t] -- conflict-free whatever the lanes' stack heights, where local memory pays one wavefront per distinct height
+// (The traversal stack of a lane in shared memory, word w of thread t at [w][t], was measured slower than local memory:
+// profiles/r02_experiments.md.)
 // FINISH and REFILL as one kind of scheduler work: measured on B200 11.52 -> 10.90 ms (the two used to cost a vote and a
 // partly filled warp iteration each: 5.3 M + 5.4 M iterations per frame at 15.7 / 17.7 lanes)
-#ifndef RTC_FUSE_RETIRE
-#define RTC_FUSE_RETIRE 1
-#endif
-#ifndef RTC_SMEM_STACK
-#define RTC_SMEM_STACK 0
-#endif
-#if RTC_SMEM_STACK
-constexpr int kStackWords = 32;  // 16 KB per block
-#define STK(i) sstk[(i) * 128 + threadIdx.x]
-#else
 constexpr int kStackWords = 56;  // per lane: inner-node stack from the bottom, noted leaves from the top
 #define STK(i) stk[i]
-#endif
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 #ifndef RTC_LEAF_FIRST
 #define RTC_LEAF_FIRST 8
@@ -209,9 +193,6 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 #define RTC_VISIT_QUORUM 16   // sweep on B200 with cone nodes: 10: 20.2, 12: 19.7, 14: 19.3, 16: 19.05 ms/step (64-byte nodes: 14 was best)
 #endif
 constexpr int kVisitQuorum = RTC_VISIT_QUORUM;
-#ifndef RTC_LAZY_OVERFLOW
-#define RTC_LAZY_OVERFLOW 1
-#endif  // at least this many lanes ready to visit: skip the full vote
 
 #ifndef RTC_TRAVERSE_MIN_BLOCKS
 #define RTC_TRAVERSE_MIN_BLOCKS 7   // 72 registers; 5 / 6 / 8 blocks (84 / 79 / 64 registers): 12.96 / 11.73 / 12.75 ms against 11.56
@@ -230,11 +211,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
     ConeDir dn{0u, 0u};
     float cd0 = 0.f;
     int sp = 0, nl = 0, k = 0;
-#if RTC_SMEM_STACK
-    __shared__ uint32_t sstk[kStackWords * 128];
-#else
     uint32_t stk[kStackWords];
-#endif
     LeafRec rec[kMaxRecords];
     uint32_t visits = 0, tests = 0, fallbacks = 0;
     uint32_t iters[4] = {0, 0, 0, 0}, busy[4] = {0, 0, 0, 0};  // STATS: warp iterations and participating lanes per kind
@@ -242,9 +219,6 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
     enum { kVisit, kLeaf, kFinish, kRefill };
     for (;;) {
         const bool room = sp + nl + (2 * (int)kNodeWidth - 1) <= kStackWords;  // a visit notes up to W leaves and pushes up to W - 1 nodes
-#if !RTC_LAZY_OVERFLOW
-        if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
-#endif
         const bool canV = active && node != kNone && room;
         const unsigned mV = __ballot_sync(kFullMask, canV);
         const int nV = __popc(mV);
@@ -253,11 +227,9 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
         unsigned mR = 0;
         int nR = 0;
         if (nV < kVisitQuorum) {  // full vote only when visiting would leave too many lanes idle
-#if RTC_LAZY_OVERFLOW
             // a lane whose stack is full of inner nodes (no noted leaf to free room) gives up and takes the
             // reference walk in FINISH; checked here only: such a lane is not in mV, so the vote comes
             if (active && node != kNone && !room && nl == 0) { overflow = true; node = kNone; sp = 0; }
-#endif
             canL = active && nl > 0;
             canF = active && node == kNone && nl == 0;
             canR = !active && (pool_left > 0 || !exhausted);
@@ -268,7 +240,6 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             nR = __popc(mR);
             // lanes holding noted leaves are served before the plain majority vote once there are enough
             // of them (threshold swept on B200: profiles/r01_experiments.md)
-#if RTC_FUSE_RETIRE
             // FINISH and REFILL are one kind of work: a lane whose ray is done stores its result and takes the next ray in
             // the same iteration (kind kFinish stands for both)
             const int nT = __popc(mF | mR);
@@ -276,14 +247,6 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             else if (nV >= nL && nV >= nT) kind = kVisit;
             else if (nL >= nT) kind = kLeaf;
             else kind = kFinish;
-#else
-            if (nL >= RTC_LEAF_FIRST) kind = kLeaf;
-            else
-            if (nV >= nL && nV >= nF && nV >= nR) kind = kVisit;
-            else if (nL >= nF && nL >= nR) kind = kLeaf;
-            else if (nF >= nR) kind = kFinish;
-            else kind = kRefill;
-#endif
         }
 
         if (STATS) {  // warp-execution efficiency of the scheduler: lanes that take part in this iteration
@@ -327,7 +290,7 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 }
             }
         } else {
-          if (kind == kFinish) {
+          if (kind == kFinish) {   // (always: FINISH and REFILL are one kind of scheduler work, the vote never picks kRefill)
             // ---- FINISH: replay of the reference recursion, store the winner
             if (canF) {
                 BestHit b;
@@ -336,15 +299,12 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
                 if (b.id != -1 && b.t < cd0) WF_ST(H.id + ray, (uint32_t)b.id);  // src/scene.cpp:68-74
                 active = false;
             }
-#if RTC_FUSE_RETIRE
             canR = !active && (pool_left > 0 || !exhausted);
             mR = __ballot_sync(kFullMask, canR);
             nR = __popc(mR);
             if (STATS) { iters[kRefill] += 1; busy[kRefill] += (uint32_t)nR; }
-#endif
           }
-          if (kind == kRefill || RTC_FUSE_RETIRE) {
-            // ---- REFILL idle lanes from the queue
+            // ---- REFILL idle lanes from the queue (the lanes that just finished among them)
             if (pool_left == 0) {
                 uint32_t base = 0;
 #if RTC_TRAVERSE_CHUNK_MAX > RTC_TRAVERSE_CHUNK
@@ -365,19 +325,12 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             uint32_t rank = __popc(mR & lt_mask);
             uint32_t serve = min((uint32_t)nR, pool_left);
             if (canR && rank < serve) {
-#if RTC_TQ_RECORDS
                 // the entry IS the ray: one coalesced round trip (consecutive ranks read consecutive 32-byte records)
                 const float4* rec32 = reinterpret_cast<const float4*>(tq) + 2 * (size_t)(pool_base + rank);
                 const float4 o4 = WF_LD(rec32), d4 = WF_LD(rec32 + 1);
                 const uint32_t entry = __float_as_uint(o4.w);
                 ray = entry & kTqSlotMask;
                 o = ld3(o4);
-#else
-                const uint32_t entry = WF_LD(tq + pool_base + rank);
-                ray = entry & kTqSlotMask;
-                o = ld3(WF_LD(P.o + ray));
-                const float4 d4 = WF_LD(P.d + ray);
-#endif
                 d = ld3(d4);
                 cd0 = d4.w;
                 inv = ray_inv(d);
@@ -405,7 +358,6 @@ __global__ void __launch_bounds__(128, RTC_TRAVERSE_MIN_BLOCKS) k_traverse(DevSc
             }
             pool_base += serve;
             pool_left -= serve;
-          }
         }
     }
     if (fallbacks) atomicAdd(stats + 5, (unsigned long long)fallbacks);

@@ -7,14 +7,11 @@
 
 namespace rtc {
 
-// Words per traverse-queue entry.  8 (RTC_TQ_RECORDS, the default): an entry is the ray itself -- (origin, bits(slot |
-// entered root children)) (direction, closest-plane distance) -- written by the kernel that makes the ray while it is
-// still in registers, so that a refill of k_traverse is ONE coalesced round trip instead of two dependent ones (queue
-// word, then the scattered path state).  1: the queue word alone.
-#ifndef RTC_TQ_RECORDS
-#define RTC_TQ_RECORDS 1
-#endif
-constexpr uint32_t kTraverseQueueWords = RTC_TQ_RECORDS ? 8 : 1;
+// Words per traverse-queue entry: an entry is the ray itself -- (origin, bits(slot | entered root children)) (direction,
+// closest-plane distance) -- written by the kernel that makes the ray while it is still in registers, so that a refill
+// of k_traverse is ONE coalesced round trip instead of two dependent ones (the queue word, then the scattered path
+// state: measured 10.58 -> 10.25 ms, profiles/r02_experiments.md).
+constexpr uint32_t kTraverseQueueWords = 8;
 
 struct LaunchCtx {
     cudaStream_t stream;
